@@ -1,0 +1,131 @@
+/* libqasr — C ABI of the B200-native Qwen3-ASR audio-encoding hot path (log-mel frontend + audio encoder).
+ *
+ * The reference (gabrimatic/qwen3-asr-mlx) has no FFI: its "operator interface" for this path is two
+ * in-process Python callables.  Each entry point below names the reference call it replaces:
+ *
+ *   qasr_mel*            log_mel_spectrogram(audio)                 src/qwen3_asr_mlx/audio.py:238-278
+ *   qasr_encode*         AudioEncoder.__call__(mel)                 src/qwen3_asr_mlx/encoder.py:235-323
+ *   qasr_encode_audio*   the back-to-back call site                 src/qwen3_asr_mlx/model.py:331-335, 418-420
+ *   qasr_create          AudioEncoder.__init__(config)              src/qwen3_asr_mlx/encoder.py:142-191
+ *   qasr_set_weight      load_encoder_weights / model.load_weights  src/qwen3_asr_mlx/encoder.py:330-359
+ *   qasr_count_tokens    AudioEncoder._conv_output_length + chunking src/qwen3_asr_mlx/encoder.py:197-207,258-268
+ *   qasr_destroy         Qwen3ASR.close()                           src/qwen3_asr_mlx/model.py:261-269
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * qasr_status; nothing throws or exits; qasr_last_error() gives the message for the last failure.
+ * A handle is bound to one CUDA device and is not thread-safe (one handle per GPU per worker).
+ * All kernels are launched on the caller-supplied stream (cudaStream_t passed as void*).
+ * There is no CPU fallback: without an sm_100 device qasr_create fails.
+ *
+ * Batched layout ("varlen packing"): B utterances are concatenated.
+ *   audio : float32[sample_offsets[B]]            utterance u = [sample_offsets[u], sample_offsets[u+1])
+ *   mel   : float32[128 * frame_offsets[B]]       utterance u = row-major (128, T_u) block at 128*frame_offsets[u],
+ *                                                 T_u = N_u / 160  (exactly the reference's (n_mels, T) array)
+ *   emb   : [token_offsets[B], output_dim]        utterance u = rows [token_offsets[u], token_offsets[u+1])
+ * Results equal a per-utterance loop over the reference (which processes one utterance at a time).
+ */
+#ifndef QASR_H_
+#define QASR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qasr_handle qasr_handle;
+
+typedef enum {
+  QASR_OK = 0,
+  QASR_ERR_INVALID = -1,      /* bad argument (maps to ValueError in the Python host) */
+  QASR_ERR_CUDA = -2,         /* CUDA runtime / driver failure */
+  QASR_ERR_UNSUPPORTED = -3,  /* configuration outside what the kernels implement, or no sm_100 device */
+  QASR_ERR_STATE = -4,        /* call sequence error (e.g. weights not finalised) */
+  QASR_ERR_NOMEM = -5
+} qasr_status;
+
+typedef enum { QASR_F32 = 0, QASR_BF16 = 1 } qasr_dtype;
+
+/* Mirrors AudioEncoderConfig (src/qwen3_asr_mlx/config.py:14-29). */
+typedef struct {
+  int32_t d_model;                 /* 1024 */
+  int32_t encoder_layers;          /* 24 */
+  int32_t encoder_attention_heads; /* 16 (head_dim must be 64) */
+  int32_t encoder_ffn_dim;         /* 4096 */
+  int32_t num_mel_bins;            /* 128 (fixed) */
+  int32_t max_source_positions;    /* 1500 */
+  int32_t output_dim;              /* 2048 */
+  int32_t n_window;                /* 50  -> chunk_size = 100 frames (fixed) */
+  int32_t n_window_infer;          /* 800 -> attention window = 13 * (800 / 100) = 104 tokens */
+  int32_t downsample_hidden_size;  /* 480 (fixed) */
+} qasr_config;
+
+typedef struct {
+  uint64_t kernel_launches;  /* kernels launched by this handle since creation */
+  uint64_t workspace_bytes;  /* device memory currently owned by the handle */
+  uint64_t weight_bytes;
+} qasr_stats;
+
+void qasr_default_config(qasr_config* cfg);
+
+int qasr_create(int device, const qasr_config* cfg, qasr_handle** out);
+void qasr_destroy(qasr_handle* h);
+/* h may be NULL: returns the message of the last failed call on this thread that had no handle. */
+const char* qasr_last_error(const qasr_handle* h);
+
+/* name: reference parameter name without the "audio_tower." prefix, e.g. "layers.3.fc1.weight".
+ * data: HOST pointer, dtype QASR_F32 or QASR_BF16, shape as stored by the reference
+ * (Linear (out,in); Conv2d (O,kH,kW,I); LayerNorm (d,)). */
+int qasr_set_weight(qasr_handle* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+/* Checks that every parameter was provided and builds the fused / re-laid-out device copies. */
+int qasr_finalize_weights(qasr_handle* h);
+
+/* T = N / 160 frames; fails with QASR_ERR_INVALID for N < 160 (the reference raises ValueError there). */
+int qasr_count_frames(int64_t n_samples, int64_t* n_frames);
+/* n = 13 * (T / 100) + f3(T % 100), f(L) = (L - 1) / 2 + 1. */
+int qasr_count_tokens(const qasr_handle* h, int64_t n_frames, int64_t* n_tokens);
+
+/* Optional: pre-size the workspace so that later calls with total_frames <= this allocate nothing. */
+int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch);
+
+/* ---- device-pointer entry points (inputs/outputs resident in HBM; offsets are HOST arrays) ---- */
+int qasr_mel(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, float* mel_dev,
+             void* stream);
+int qasr_encode(qasr_handle* h, const float* mel_dev, const int64_t* frame_offsets, int32_t batch, void* emb_dev,
+                int out_dtype, int64_t* token_offsets_out, void* stream);
+/* mel + encoder back to back (the mel lives in handle-owned scratch). */
+int qasr_encode_audio(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch,
+                      void* emb_dev, int out_dtype, int64_t* token_offsets_out, void* stream);
+
+/* ---- host-pointer entry points (H2D / D2H inside the call, synchronous on return) ---- */
+int qasr_mel_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
+                  float* mel_host);
+int qasr_encode_host(qasr_handle* h, const float* mel_host, const int64_t* frame_offsets, int32_t batch,
+                     void* emb_host, int out_dtype, int64_t* token_offsets_out);
+int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
+                           void* emb_host, int out_dtype, int64_t* token_offsets_out);
+
+/* ---- constant tables, as the library builds them (for parity tests) ---- */
+int qasr_mel_filterbank(float* out_128x201);
+int qasr_hann_window(float* out_400);
+int qasr_positional_embedding(const qasr_handle* h, int32_t rows, float* out_rows_x_dmodel);
+
+int qasr_get_stats(const qasr_handle* h, qasr_stats* out);
+
+/* ---- test hooks ---- */
+/* When enabled, qasr_encode keeps copies of intermediate activations for qasr_debug_read. */
+int qasr_set_debug(qasr_handle* h, int enabled);
+/* what: "stem" (fp32 [n_tok, d_model] after conv stem + PE + packing),
+ *       "layer0" (fp32 [n_tok, d_model] after the first transformer layer),
+ *       "hidden" (fp32 [n_tok, d_model] after the last layer, before ln_post). */
+int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_floats);
+/* Stand-alone dense GEMM through the encoder's tcgen05 kernel: out[M,N] = a[M,K] * w[N,K]^T (+bias),
+ * a/w bf16 HOST arrays, out fp32 HOST array.  mode: 0 store, 1 gelu. */
+int qasr_test_gemm(int device, const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, int32_t M,
+                   int32_t N, int32_t K, int32_t mode, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QASR_H_ */

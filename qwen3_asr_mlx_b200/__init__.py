@@ -1,0 +1,25 @@
+"""qwen3_asr_mlx_b200: B200-native Qwen3-ASR audio-encoding hot path (log-mel frontend + audio encoder).
+
+Drop-in for that path of gabrimatic/qwen3-asr-mlx: the names exported here are the reference's
+(src/qwen3_asr_mlx/__init__.py:16-37) for everything on the path; compute runs in libqasr
+(hand-written sm_100a CUDA behind a C ABI, include/qasr.h).
+"""
+
+__version__ = "0.1.0"
+
+from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
+from .config import AudioEncoderConfig
+from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
+from ._array import DeviceArray
+
+__all__ = [
+    "__version__",
+    "load_audio",
+    "log_mel_spectrogram",
+    "log_mel_spectrogram_batch",
+    "AudioEncoderConfig",
+    "AudioEncoder",
+    "SinusoidalPositionEmbedding",
+    "load_encoder_weights",
+    "DeviceArray",
+]

@@ -1,0 +1,300 @@
+// Non-GEMM kernels of the audio encoder path:
+//   conv1_gelu_kernel      Conv2d(1->C, k3, s2, p1) + bias + GELU on 100-frame mel chunks
+//                          (reference encoder.py:258-273), output written straight into the
+//                          parity-plane layout the conv2 implicit GEMM consumes
+//   layernorm_bf16_kernel  LayerNorm(eps=1e-5, affine) fp32 -> bf16 (encoder.py:112,117,319)
+//   window_attention_kernel block-diagonal (<=104-token windows) multi-head attention
+//                          (encoder.py:78-85,297-311) over varlen-packed tokens; the O(n^2)
+//                          additive mask of the reference is never materialised.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "math.cuh"
+#include "ptx.cuh"
+
+namespace qasr {
+
+// ------------------------------------------------------------------------------ conv1
+struct ChunkDesc {
+  long long mel_base;  // float offset of this utterance's (128, T) block in the packed mel buffer
+  int T;               // frames in the utterance
+  int frame0;          // first frame of this chunk
+};
+
+constexpr int kConv1Threads = 240;    // 60 channel groups (8 ch) x 4 pixel slots (C = 480)
+constexpr int kConv1RowsPerCta = 8;   // output rows per CTA  (64 / 8 = 8 CTAs per chunk)
+
+// planes layout: [4][rows_total = G*33][26][C] bf16, plane = 2*(h&1) + (w&1), pixel (h,w) of
+// the 64x50 conv1 output stored at row b*33 + h/2 + 1, column w/2 + 1 (row/column 0 = zero pad).
+template <int C>
+__global__ void __launch_bounds__(kConv1Threads)
+conv1_gelu_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ chunks, int chunk0,
+                  const float* __restrict__ w /*[C][9]*/, const float* __restrict__ bias /*[C]*/,
+                  __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+  static_assert(C % 8 == 0 && (C / 8) * 4 == kConv1Threads, "thread mapping assumes C == 480");
+  constexpr int IW = 104;  // smem row pitch
+  __shared__ float in[2 * kConv1RowsPerCta + 1][IW];
+
+  const int b = blockIdx.x / (64 / kConv1RowsPerCta);      // chunk within the group
+  const int part = blockIdx.x % (64 / kConv1RowsPerCta);
+  const int oh0 = part * kConv1RowsPerCta;
+  const ChunkDesc cd = chunks[chunk0 + b];
+  const float* __restrict__ src = mel + cd.mel_base;
+  const int valid_w = min(100, cd.T - cd.frame0);
+
+  // stage input rows h = 2*oh0-1 .. 2*oh0+15, columns w = -1 .. 100 (zero outside the chunk / utterance)
+  for (int i = threadIdx.x; i < (2 * kConv1RowsPerCta + 1) * 102; i += kConv1Threads) {
+    const int r = i / 102, c = i - r * 102;
+    const int h = 2 * oh0 - 1 + r, wv = c - 1;
+    float v = 0.0f;
+    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+    in[r][c] = v;
+  }
+
+  const int cg = threadIdx.x % (C / 8);
+  const int slot = threadIdx.x / (C / 8);
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = __ldg(bias + cg * 8 + c);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (cg * 8 + c) * 9 + t);
+  }
+  __syncthreads();
+
+  for (int p = slot; p < kConv1RowsPerCta * 50; p += 4) {
+    const int ohl = p / 50, ow = p - ohl * 50;
+    float patch[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) patch[kh * 3 + kw] = in[2 * ohl + kh][2 * ow + kw];
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = br[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], patch[t], a);
+      acc[c] = gelu_fast(a);
+    }
+    const int h = oh0 + ohl;
+    const int plane = 2 * (h & 1) + (ow & 1);
+    const long long pix = (static_cast<long long>(b) * 33 + (h >> 1) + 1) * 26 + (ow >> 1) + 1;
+    uint4 q;
+    q.x = ptx::pack_bf16x2(acc[0], acc[1]);
+    q.y = ptx::pack_bf16x2(acc[2], acc[3]);
+    q.z = ptx::pack_bf16x2(acc[4], acc[5]);
+    q.w = ptx::pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(planes + plane * plane_stride + pix * C + cg * 8) = q;
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+// One warp per row; VPL float4 per lane (D = 128 * VPL); two-pass statistics in registers.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __nv_bfloat16* __restrict__ y, int rows, float eps) {
+  constexpr int D = 128 * VPL;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* __restrict__ xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  float4 v[VPL];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* __restrict__ b4 = reinterpret_cast<const float4*>(beta);
+  uint2* __restrict__ yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * D);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+    uint2 o;
+    o.x = ptx::pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+    o.y = ptx::pack_bf16x2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    yr[lane + 32 * i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------ attention
+// One CTA per (window, head).  Window = up to 104 consecutive packed tokens of one utterance.
+// qkv: [n_tok, 3*D] bf16 (q | k | v), head h occupies columns h*64 .. h*64+63 of each third.
+// Each of 7 warps owns 16 query rows; S = Q K^T and O = P V run on mma.sync.m16n8k16 bf16
+// with fp32 accumulation; the softmax is single-pass in registers (a window fits entirely).
+constexpr int kAttnMaxWin = 112;   // 104 rounded up to a multiple of 16
+constexpr int kAttnThreads = 224;  // 7 warps
+constexpr int kAttnPitch = 72;     // bf16 per smem row (64 + 8 pad: conflict-free ldmatrix)
+
+struct WindowDesc {
+  int start;  // first token (row of qkv / out)
+  int len;    // tokens in the window (1..104)
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const WindowDesc* __restrict__ windows,
+                        __nv_bfloat16* __restrict__ out, int D, float scale_log2e) {
+  __shared__ __align__(16) __nv_bfloat16 sK[kAttnMaxWin * kAttnPitch];
+  __shared__ __align__(16) __nv_bfloat16 sV[kAttnMaxWin * kAttnPitch];
+
+  const WindowDesc wd = windows[blockIdx.x];
+  const int head = blockIdx.y;
+  const int len = wd.len;
+  const int nk16 = (len + 15) >> 4;  // 16-key blocks
+  const long long ld = 3LL * D;
+  const __nv_bfloat16* __restrict__ base = qkv + static_cast<long long>(wd.start) * ld + head * 64;
+
+  // stage K and V (zero rows beyond len so that masked probabilities multiply finite values)
+  for (int i = threadIdx.x; i < nk16 * 16 * 8; i += kAttnThreads) {
+    const int r = i >> 3, c = i & 7;  // 8 x 16-byte vectors per 64-wide row
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (r < len) {
+      kv = *reinterpret_cast<const uint4*>(base + r * ld + D + c * 8);
+      vv = *reinterpret_cast<const uint4*>(base + r * ld + 2 * D + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + r * kAttnPitch + c * 8) = kv;
+    *reinterpret_cast<uint4*>(sV + r * kAttnPitch + c * 8) = vv;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16;
+  if (row0 >= len) return;
+
+  // Q fragments straight from global (each row is used by exactly one warp)
+  uint32_t qa[4][4];
+  {
+    const int r_lo = row0 + g, r_hi = row0 + g + 8;
+    const __nv_bfloat16* q_lo = base + static_cast<long long>(min(r_lo, len - 1)) * ld;
+    const __nv_bfloat16* q_hi = base + static_cast<long long>(min(r_hi, len - 1)) * ld;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      qa[kk][0] = *reinterpret_cast<const uint32_t*>(q_lo + kk * 16 + 2 * t);
+      qa[kk][1] = *reinterpret_cast<const uint32_t*>(q_hi + kk * 16 + 2 * t);
+      qa[kk][2] = *reinterpret_cast<const uint32_t*>(q_lo + kk * 16 + 8 + 2 * t);
+      qa[kk][3] = *reinterpret_cast<const uint32_t*>(q_hi + kk * 16 + 8 + 2 * t);
+    }
+  }
+
+  // S = Q K^T : 14 key tiles of 8
+  float s[14][4];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f; }
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    if (j < 2 * nk16) {
+      // matrices: (keys 8j.., dims 0-7), (dims 8-15), (dims 16-23), (dims 24-31) then dims 32-63
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t kb[4];
+        const int mrow = 8 * j + (lane & 7);
+        const int mcol = half * 32 + (lane >> 3) * 8;
+        ldmatrix_x4(kb, sK + mrow * kAttnPitch + mcol);
+        mma_bf16_16816(s[j], qa[2 * half + 0], kb[0], kb[1]);
+        mma_bf16_16816(s[j], qa[2 * half + 1], kb[2], kb[3]);
+      }
+    }
+  }
+
+  // softmax over keys (rows g and g+8 of this warp's slab)
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    const int c0 = 8 * j + 2 * t;
+    if (c0 >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+    if (c0 + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+    mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+  }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  float sum_lo = 0.0f, sum_hi = 0.0f;
+  uint32_t pa[7][4];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    const float p0 = exp2f((s[j][0] - mx_lo) * scale_log2e);
+    const float p1 = exp2f((s[j][1] - mx_lo) * scale_log2e);
+    const float p2 = exp2f((s[j][2] - mx_hi) * scale_log2e);
+    const float p3 = exp2f((s[j][3] - mx_hi) * scale_log2e);
+    sum_lo += p0 + p1;
+    sum_hi += p2 + p3;
+    pa[j >> 1][(j & 1) * 2 + 0] = ptx::pack_bf16x2(p0, p1);
+    pa[j >> 1][(j & 1) * 2 + 1] = ptx::pack_bf16x2(p2, p3);
+  }
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+
+  // O = P V : 8 dim tiles of 8
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f; }
+#pragma unroll
+  for (int kk = 0; kk < 7; ++kk) {
+    if (kk < nk16) {
+#pragma unroll
+      for (int jn = 0; jn < 8; jn += 2) {
+        // matrices: (keys 16kk+0..7, dims 8jn..), (keys +8..15, dims 8jn..), same for jn+1
+        uint32_t vb[4];
+        const int mrow = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int mcol = 8 * jn + (lane >> 4) * 8;
+        ldmatrix_x4_trans(vb, sV + mrow * kAttnPitch + mcol);
+        mma_bf16_16816(o[jn], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[jn + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+  }
+
+  const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  __nv_bfloat16* __restrict__ obase = out + static_cast<long long>(wd.start) * D + head * 64;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (r_lo < len)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(r_lo) * D + 8 * j + 2 * t) =
+          ptx::pack_bf16x2(o[j][0] * inv_lo, o[j][1] * inv_lo);
+    if (r_hi < len)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(r_hi) * D + 8 * j + 2 * t) =
+          ptx::pack_bf16x2(o[j][2] * inv_hi, o[j][3] * inv_hi);
+  }
+}
+
+}  // namespace qasr

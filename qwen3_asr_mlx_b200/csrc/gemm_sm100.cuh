@@ -1,0 +1,316 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (+ epilogue)
+//
+//   warp 0      TMA producer      (one elected lane; cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      MMA issuer        (one elected lane; tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warp 3      idle
+//   warps 4-11  epilogue          (tcgen05.ld -> registers -> bias / GELU / residual / scatter -> global)
+//
+// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the
+// main loop of tile i+1.  The same kernel serves every dense contraction on the encoder
+// path (reference call sites: encoder.py:74-76,86 q/k/v/out_proj; :118-119 fc1/fc2;
+// :279 conv_out; :320-321 proj1/proj2) and, with kAMode == A_CONV, the stride-2 3x3
+// convolutions conv2d2/conv2d3 (encoder.py:274-275) as an implicit GEMM whose A operand is
+// gathered by 4-D TMA boxes from a parity-split ("space-to-depth") activation layout, so
+// that every filter tap is a unit-stride box and zero padding is a physical zero border.
+#pragma once
+#include "math.cuh"
+#include "ptx.cuh"
+
+namespace qasr {
+
+enum AMode : int { A_ROWS = 0, A_CONV = 1 };
+enum EpiMode : int {
+  EPI_STORE_BF16 = 0,    // out_bf16[m,n] = acc + bias
+  EPI_GELU_BF16 = 1,     // out_bf16[m,n] = gelu(acc + bias)
+  EPI_RESID_F32 = 2,     // out_f32[m,n] += acc + bias          (residual stream, in place)
+  EPI_STORE_F32 = 3,     // out_f32[m,n] = acc + bias
+  EPI_CONV_PLANES = 4,   // gelu(acc+bias) -> bf16, scattered into the next conv's parity planes
+  EPI_CONV_FLAT = 5,     // gelu(acc+bias) -> bf16, [(chunk*OW + ow)*OH + oh][ch]  (conv_out's A operand)
+  EPI_CONVOUT_PACK = 6,  // out_f32[row_map[m], n] = acc + pe[m % period, n]  (PE add + strip padding + pack)
+  EPI_GELU_F32 = 7       // out_f32[m,n] = gelu(acc + bias)
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 384;
+constexpr int kNumEpiWarps = 8;
+constexpr int kAccumStride = 256;  // TMEM columns per accumulator stage
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  void* out;
+  long long ldo;  // elements
+  const float* bias;
+  // implicit-GEMM convolution geometry (kAMode == A_CONV)
+  int conv_OW;             // output width (pixels per output row)
+  int conv_OH;             // real output rows per chunk
+  int conv_OHp;            // padded output rows per chunk (= OH + 1, the extra row is a dummy)
+  int conv_rows_per_tile;  // output rows per M tile (rows_per_tile * OW <= 128)
+  int conv_kc_per_tap;     // K blocks per filter tap (ceil(C / 64))
+  int conv_chunks;         // number of real chunks
+  // EPI_CONV_PLANES destination geometry
+  int out_Hp, out_Wp;             // padded rows per chunk / padded width of destination planes
+  long long out_plane_stride;     // elements between destination planes
+  int out_C;                      // channels per pixel in the destination
+  // EPI_CONVOUT_PACK
+  const int* row_map;  // [M] destination row or -1
+  const float* pe;     // [period, N]
+  int pe_period;
+};
+
+template <int BLOCK_N, int kStages>
+struct GemmSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+};
+
+template <int kEpi, int W>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[W], const GemmParams& p, int n, void* row_ptr,
+                                               int pe_row) {
+  // row_ptr points at element (dest_row, 0) of the destination; n is the absolute column.
+  float v[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = __uint_as_float(acc[i]);
+  if constexpr (kEpi == EPI_CONVOUT_PACK) {
+    const float4* pe4 = reinterpret_cast<const float4*>(p.pe + static_cast<long long>(pe_row) * p.N + n);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+      float4 t = __ldg(pe4 + i);
+      v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  } else {
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        float4 t = __ldg(b4 + i);
+        v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+      }
+    }
+  }
+  if constexpr (kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = gelu_fast(v[i]);  // output is rounded to bf16 below
+  } else if constexpr (kEpi == EPI_GELU_F32) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if constexpr (kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES ||
+                kEpi == EPI_CONV_FLAT) {
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(row_ptr) + n);
+#pragma unroll
+    for (int i = 0; i < W / 8; ++i) {
+      uint4 q;
+      q.x = ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      q.y = ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      q.z = ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      q.w = ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      dst[i] = q;
+    }
+  } else if constexpr (kEpi == EPI_RESID_F32) {
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+      float4 t = dst[i];
+      t.x += v[4 * i + 0]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
+      dst[i] = t;
+    }
+  } else {  // EPI_STORE_F32, EPI_CONVOUT_PACK, EPI_GELU_F32
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) dst[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+
+template <int BLOCK_N, int kStages, int kAMode, int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmParams p) {
+  using L = GemmSmem<BLOCK_N, kStages>;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert((L::kBBytes % 1024) == 0, "B stage must keep 1024-byte alignment");
+  constexpr int kChunk = (BLOCK_N % 32 == 0) ? 32 : 16;  // epilogue column granularity
+  constexpr int kNumChunks = BLOCK_N / kChunk;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    ptx::tmem_alloc<1>(tmem_ptr_smem, 2 * kAccumStride);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          void* sa = smem_a + stage * L::kABytes;
+          void* sb = smem_b + stage * L::kBBytes;
+          if constexpr (kAMode == A_ROWS) {
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
+          } else {
+            const int tap = kb / p.conv_kc_per_tap;
+            const int kc = kb - tap * p.conv_kc_per_tap;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const int plane = 2 * (kh != 1) + (kw != 1);
+            const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
+            ptx::tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * kBlockK, (kw != 0), row0, plane);
+            ptx::tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBlockK, tap, n_blk * BLOCK_N);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccumStride;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
+            ptx::umma_bf16_ss<1>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp_idx - 4;
+    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;          // interleaved column chunks
+    const int r = quarter * 32 + lane;  // tile row == TMEM lane
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile % p.num_n_tiles;
+      const int n0 = n_blk * BLOCK_N;
+
+      // Resolve this thread's destination row once per tile.
+      void* row_ptr = nullptr;
+      int pe_row = 0;
+      if constexpr (kAMode == A_ROWS) {
+        const int m = m_blk * kBlockM + r;
+        if (m < p.M) {
+          if constexpr (kEpi == EPI_CONVOUT_PACK) {
+            const int dst = __ldg(p.row_map + m);
+            pe_row = m % p.pe_period;
+            if (dst >= 0) row_ptr = static_cast<float*>(p.out) + static_cast<long long>(dst) * p.ldo;
+          } else if constexpr (kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16) {
+            row_ptr = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo;
+          } else {
+            row_ptr = static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo;
+          }
+        }
+      } else {
+        // tile row r -> (padded output row, ow) -> (chunk, oh, ow)
+        const int rr = r / p.conv_OW;
+        const int ow = r - rr * p.conv_OW;
+        if (rr < p.conv_rows_per_tile) {
+          const int g = m_blk * p.conv_rows_per_tile + rr;
+          const int b = g / p.conv_OHp;
+          const int oh = g - b * p.conv_OHp;
+          if (b < p.conv_chunks && oh < p.conv_OH) {
+            if constexpr (kEpi == EPI_CONV_PLANES) {
+              const int plane = 2 * (oh & 1) + (ow & 1);
+              const long long pix =
+                  (static_cast<long long>(b) * p.out_Hp + (oh >> 1) + 1) * p.out_Wp + (ow >> 1) + 1;
+              row_ptr = static_cast<__nv_bfloat16*>(p.out) + plane * p.out_plane_stride + pix * p.out_C;
+            } else {  // EPI_CONV_FLAT
+              const long long pix = (static_cast<long long>(b) * p.conv_OW + ow) * p.conv_OH + oh;
+              row_ptr = static_cast<__nv_bfloat16*>(p.out) + pix * p.out_C;
+            }
+          }
+        }
+      }
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccumStride;
+#pragma unroll 1
+      for (int j = half; j < kNumChunks; j += 2) {
+        uint32_t acc[kChunk];
+        if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + j * kChunk, acc);
+        else ptx::tmem_ld_32x16(taddr + j * kChunk, acc);
+        ptx::tmem_ld_wait();
+        const int n = n0 + j * kChunk;
+        if (row_ptr != nullptr && n < p.N) epilogue_chunk<kEpi, kChunk>(acc, p, n, row_ptr, pe_row);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 2 * kAccumStride);
+  }
+}
+
+}  // namespace qasr

@@ -1,0 +1,251 @@
+// Log-mel frontend kernels (reference: log_mel_spectrogram, audio.py:238-278; _stft :211-235;
+// _build_mel_filterbank :41-80).
+//
+// Pass 1 (mel_logmel_kernel): one CTA per 32 frames of one utterance.
+//   reflect-padded framing -> symmetric Hann window -> 400-point real FFT (16 x 25, fp32,
+//   see mel_fft.cuh) -> power -> banded mel filterbank -> log10(max(., 1e-10)) -> packed
+//   (128, T_u) fp32 output + per-utterance running max (ordered-uint atomicMax).
+// Pass 2 (mel_normalize_kernel): max(x, utt_max - 8) then (x + 4) / 4, in place.
+//
+// Layout: audio of B utterances packed back to back (sample_offsets[B+1]); mel of utterance
+// u is a row-major (128, T_u) block starting at float offset 128 * frame_offsets[u].
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "mel_fft.cuh"
+
+namespace qasr {
+
+constexpr int kMelNfft = 400;
+constexpr int kMelHop = 160;
+constexpr int kMelBins = 128;
+constexpr int kMelFreqs = 201;
+constexpr int kMelMaxTaps = 12;       // max non-zeros per filter row we store (reference: <= 9)
+constexpr int kMelFramesPerCta = 32;
+constexpr int kMelThreads = 256;
+
+struct MelTables {
+  const float* window;     // [400]  symmetric Hann, float32 (np.hanning(400).astype(f32))
+  const float2* twiddle;   // [9][25] W400^{n2*k1}
+  const int* fb_start;     // [128] first non-zero frequency bin of each filter
+  const int* fb_count;     // [128] number of stored taps
+  const float* fb_weight;  // [128][kMelMaxTaps]
+};
+
+// ---------------------------------------------------------------- host: table construction
+// Mirrors _build_mel_filterbank (audio.py:41-80): HTK mel formula, triangular filters on
+// linspace(0, sr/2, 201), slopes rounded to float32, then divided by the filter width in Hz.
+inline void build_mel_filterbank_host(std::vector<float>& fb /*128*201*/, int n_fft = 400, int n_mels = 128,
+                                      double sr = 16000.0, double f_min = 0.0, double f_max = 8000.0) {
+  const int n_freqs = n_fft / 2 + 1;
+  fb.assign(static_cast<size_t>(n_mels) * n_freqs, 0.0f);
+  std::vector<double> freqs(n_freqs), fpts(n_mels + 2);
+  const double fstep = (sr / 2.0 - 0.0) / (n_freqs - 1);
+  for (int k = 0; k < n_freqs; ++k) freqs[k] = k * fstep + 0.0;
+  freqs[n_freqs - 1] = sr / 2.0;
+  const double mel_min = 2595.0 * log10(1.0 + f_min / 700.0);
+  const double mel_max = 2595.0 * log10(1.0 + f_max / 700.0);
+  const double mstep = (mel_max - mel_min) / (n_mels + 1);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    double m = i * mstep + mel_min;
+    if (i == n_mels + 1) m = mel_max;
+    fpts[i] = 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+  }
+  for (int i = 0; i < n_mels; ++i) {
+    const double fl = fpts[i], fc = fpts[i + 1], fr = fpts[i + 2];
+    const double width = fr - fl;
+    for (int k = 0; k < n_freqs; ++k) {
+      const double up = (freqs[k] - fl) / (fc - fl);
+      const double down = (fr - freqs[k]) / (fr - fc);
+      const double v = fmax(0.0, fmin(up, down));
+      float f32 = static_cast<float>(v);
+      if (width > 0.0) f32 = static_cast<float>(static_cast<double>(f32) / width);
+      fb[static_cast<size_t>(i) * n_freqs + k] = f32;
+    }
+  }
+}
+
+inline void build_hann_window_host(std::vector<float>& w, int n = 400) {
+  // np.hanning(n): 0.5 - 0.5 cos(2 pi i / (n - 1)), computed in float64 then cast.
+  w.resize(n);
+  for (int i = 0; i < n; ++i) {
+    // numpy evaluates hanning on n = arange(1-M, M, 2): 0.5 + 0.5*cos(pi*n/(M-1))
+    const double nn = static_cast<double>(1 - n + 2 * i);
+    w[i] = static_cast<float>(0.5 + 0.5 * cos(M_PI * nn / (n - 1)));
+  }
+}
+
+inline void build_twiddle_host(std::vector<float2>& tw) {
+  tw.resize(9 * 25);
+  for (int k1 = 0; k1 < 9; ++k1)
+    for (int n2 = 0; n2 < 25; ++n2) {
+      const double a = -2.0 * M_PI * static_cast<double>(n2 * k1) / 400.0;
+      tw[k1 * 25 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+    }
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// np.pad(mode="reflect") index map (period 2(N-1)); valid for any integer i when N >= 2.
+__device__ __forceinline__ long long reflect_index(long long i, long long n) {
+  const long long period = 2 * (n - 1);
+  long long m = i % period;
+  if (m < 0) m += period;
+  return (m < n) ? m : period - m;
+}
+// largest u in [0, B) with offs[u] <= v   (offs is non-decreasing, offs[0] = 0)
+template <typename T>
+__device__ __forceinline__ int upper_segment(const T* __restrict__ offs, int B, T v) {
+  int lo = 0, hi = B;  // invariant: offs[lo] <= v < offs[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(offs + mid) <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+struct MelSmem {
+  float raw[(kMelFramesPerCta - 1) * kMelHop + kMelNfft];  // 5360
+  float window[kMelNfft];
+  float2 twiddle[9 * 25];
+  float2 Y[kMelFramesPerCta][9][25];
+  float P[kMelFreqs][kMelFramesPerCta + 1];
+  float red[kMelThreads / 32];
+};
+
+__global__ void __launch_bounds__(kMelThreads)
+mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ sample_offsets,
+                  const long long* __restrict__ frame_offsets, const int* __restrict__ block_offsets, int B,
+                  MelTables tab, float* __restrict__ mel_out, unsigned* __restrict__ utt_max) {
+  extern __shared__ __align__(16) uint8_t mel_smem_raw[];
+  MelSmem& s = *reinterpret_cast<MelSmem*>(mel_smem_raw);
+  const int tid = threadIdx.x;
+
+  const int u = upper_segment<int>(block_offsets, B, static_cast<int>(blockIdx.x));
+  const long long s0 = __ldg(sample_offsets + u);
+  const long long N = __ldg(sample_offsets + u + 1) - s0;
+  const long long f0 = __ldg(frame_offsets + u);
+  const int T = static_cast<int>(__ldg(frame_offsets + u + 1) - f0);
+  const int t0 = (static_cast<int>(blockIdx.x) - __ldg(block_offsets + u)) * kMelFramesPerCta;
+  const int nf = min(kMelFramesPerCta, T - t0);
+
+  // ---- stage tables and the reflect-padded sample span of these frames
+  for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
+  for (int i = tid; i < 9 * 25; i += kMelThreads) s.twiddle[i] = __ldg(tab.twiddle + i);
+  const int span = (nf - 1) * kMelHop + kMelNfft;
+  const long long first = static_cast<long long>(t0) * kMelHop - kMelNfft / 2;
+  const float* __restrict__ x = audio + s0;
+  for (int i = tid; i < span; i += kMelThreads) {
+    long long j = first + i;
+    if (j < 0 || j >= N) j = reflect_index(j, N);
+    s.raw[i] = __ldg(x + j);
+  }
+  __syncthreads();
+
+  // ---- step A/B: 25 real 16-point DFTs per frame, twiddled
+  for (int task = tid; task < nf * 25; task += kMelThreads) {
+    const int f = task / 25, n2 = task - f * 25;
+    const float* fr = s.raw + f * kMelHop + n2;
+    float v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = fr[25 * n1] * s.window[25 * n1 + n2];
+    fft::cf y[9];
+    fft::rdft16(v, y);
+#pragma unroll
+    for (int k1 = 0; k1 < 9; ++k1) {
+      const float2 w = s.twiddle[k1 * 25 + n2];
+      s.Y[f][k1][n2] = make_float2(y[k1].re * w.x - y[k1].im * w.y, y[k1].re * w.y + y[k1].im * w.x);
+    }
+  }
+  __syncthreads();
+
+  // ---- step C: 9 complex 25-point DFTs per frame -> power spectrum P[bin][frame]
+  for (int task = tid; task < nf * 9; task += kMelThreads) {
+    const int f = task / 9, k1 = task - f * 9;
+    fft::cf z[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) {
+      const float2 t = s.Y[f][k1][i];
+      z[i] = {t.x, t.y};
+    }
+    fft::dft25(z);
+    const bool self_conj = (k1 == 0) || (k1 == 8);
+#pragma unroll
+    for (int k2 = 0; k2 < 25; ++k2) {
+      const int k = k1 + 16 * k2;
+      const float pw = z[k2].re * z[k2].re + z[k2].im * z[k2].im;
+      if (k <= 200) s.P[k][f] = pw;
+      else if (!self_conj) s.P[400 - k][f] = pw;
+    }
+  }
+  __syncthreads();
+
+  // ---- banded mel filterbank + log10, frame index fastest (coalesced 128-byte rows)
+  float lmax = -INFINITY;
+  float* __restrict__ out = mel_out + f0 * kMelBins;
+  for (int task = tid; task < kMelBins * kMelFramesPerCta; task += kMelThreads) {
+    const int m = task / kMelFramesPerCta, f = task - m * kMelFramesPerCta;
+    if (f < nf) {
+      const int st = __ldg(tab.fb_start + m), cnt = __ldg(tab.fb_count + m);
+      const float* __restrict__ w = tab.fb_weight + m * kMelMaxTaps;
+      float acc = 0.0f;
+      for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), s.P[st + j][f], acc);
+      const float v = log10f(fmaxf(acc, 1e-10f));
+      out[static_cast<long long>(m) * T + t0 + f] = v;
+      lmax = fmaxf(lmax, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) s.red[tid >> 5] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s.red[0];
+#pragma unroll
+    for (int i = 1; i < kMelThreads / 32; ++i) m = fmaxf(m, s.red[i]);
+    atomicMax(utt_max + u, float_to_ordered(m));
+  }
+}
+
+// Pass 2: x = (max(x, utt_max - 8) + 4) / 4 over the packed mel buffer (float4 granularity:
+// every utterance block is a multiple of 128 floats).
+constexpr int kMelNormThreads = 256;
+constexpr int kMelNormVecPerCta = 2048;  // float4 per CTA
+
+__global__ void __launch_bounds__(kMelNormThreads)
+mel_normalize_kernel(float* __restrict__ mel, const long long* __restrict__ frame_offsets, int B,
+                     const unsigned* __restrict__ utt_max, long long total_vec4) {
+  const long long base = static_cast<long long>(blockIdx.x) * kMelNormVecPerCta;
+  // utterance of the first element of this CTA (element e belongs to u iff 128*fo[u] <= 4e < 128*fo[u+1])
+  int u = upper_segment<long long>(frame_offsets, B, (base * 4) / kMelBins);
+  long long end_vec = __ldg(frame_offsets + u + 1) * (kMelBins / 4);
+  float thr = ordered_to_float(__ldg(utt_max + u)) - 8.0f;
+  float4* __restrict__ p = reinterpret_cast<float4*>(mel);
+  for (int i = threadIdx.x; i < kMelNormVecPerCta; i += kMelNormThreads) {
+    const long long e = base + i;
+    if (e >= total_vec4) break;
+    while (e >= end_vec) {
+      ++u;
+      end_vec = __ldg(frame_offsets + u + 1) * (kMelBins / 4);
+      thr = ordered_to_float(__ldg(utt_max + u)) - 8.0f;
+    }
+    float4 v = p[e];
+    v.x = (fmaxf(v.x, thr) + 4.0f) * 0.25f;
+    v.y = (fmaxf(v.y, thr) + 4.0f) * 0.25f;
+    v.z = (fmaxf(v.z, thr) + 4.0f) * 0.25f;
+    v.w = (fmaxf(v.w, thr) + 4.0f) * 0.25f;
+    p[e] = v;
+  }
+}
+
+}  // namespace qasr

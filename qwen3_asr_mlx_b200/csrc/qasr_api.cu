@@ -1,0 +1,904 @@
+// libqasr: C-ABI implementation (include/qasr.h).  Handle / weights / workspace management and the
+// launch sequence of the audio-encoding hot path.  No CPU fallback exists: every compute step
+// below is a kernel from mel.cuh, encoder_kernels.cuh or gemm_sm100.cuh.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qasr.h"
+#include "encoder_kernels.cuh"
+#include "gemm_host.cuh"
+#include "mel.cuh"
+
+using namespace qasr;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+constexpr int kChunkFrames = 100;     // n_window * 2 (encoder.py:145)
+constexpr int kTokensPerChunk = 13;   // f^3(100)
+constexpr int kStemC = 480;
+constexpr int kStemGroupDefault = 1024;
+constexpr int kGemmStages = 4;
+
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline int conv_len3(int L) {
+  for (int i = 0; i < 3; ++i) L = (L - 1) / 2 + 1;
+  return L;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct LayerWeights {
+  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+};
+
+}  // namespace
+
+struct qasr_handle {
+  int device = 0;
+  qasr_config cfg{};
+  std::string err;
+  bool finalized = false;
+  bool debug = false;
+  qasr_stats stats{};
+
+  std::map<std::string, std::vector<float>> staged;  // host copies until finalize
+  std::vector<void*> weight_allocs;
+
+  // mel tables
+  float* d_window = nullptr;
+  float2* d_twiddle = nullptr;
+  int* d_fb_start = nullptr;
+  int* d_fb_count = nullptr;
+  float* d_fb_weight = nullptr;
+
+  // encoder weights
+  float *conv1_w = nullptr, *conv1_b = nullptr, *conv2_b = nullptr, *conv3_b = nullptr;
+  __nv_bfloat16 *conv2_w = nullptr, *conv3_w = nullptr, *convout_w = nullptr, *proj1_w = nullptr, *proj2_w = nullptr;
+  float *proj1_b = nullptr, *proj2_b = nullptr, *lnp_g = nullptr, *lnp_b = nullptr, *pe = nullptr;
+  CUtensorMap tm_conv2_w, tm_conv3_w, tm_convout_w, tm_proj1_w, tm_proj2_w;
+  std::vector<LayerWeights> layers;
+
+  // workspace (grow-only)
+  int stem_group = kStemGroupDefault;
+  long long cap_group = 0, cap_tokens = 0, cap_chunks = 0, cap_windows = 0, cap_batch = 0, cap_mel_frames = 0;
+  long long cap_io_in = 0, cap_io_out = 0;
+  DevBuf planes1, planes2, flat3, x, xn, qkv, attn, hbuf, mel_scratch, io_in, io_out;
+  DevBuf d_chunks, d_rowmap, d_windows, d_soffs, d_foffs, d_boffs, d_uttmax;
+  DevBuf dbg_stem, dbg_layer0, dbg_hidden;
+  long long dbg_tokens = 0;
+  CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1;
+  // pinned staging for tables
+  void* pin = nullptr;
+  size_t pin_bytes = 0;
+  cudaEvent_t pin_event = nullptr;
+  bool pin_event_pending = false;
+};
+
+namespace {
+
+int fail(qasr_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return code;
+}
+#define QCUDA(h, expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(h, QASR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+int dev_alloc(qasr_handle* h, DevBuf& b, size_t bytes, bool zero) {
+  if (bytes <= b.bytes) return QASR_OK;
+  if (b.p) {
+    QCUDA(h, cudaFree(b.p));
+    h->stats.workspace_bytes -= b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(h, QASR_ERR_NOMEM, "cudaMalloc(" + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+  }
+  b.bytes = bytes;
+  h->stats.workspace_bytes += bytes;
+  if (zero) QCUDA(h, cudaMemset(b.p, 0, bytes));
+  return QASR_OK;
+}
+void dev_free(qasr_handle* h, DevBuf& b) {
+  if (b.p) {
+    cudaFree(b.p);
+    h->stats.workspace_bytes -= b.bytes;
+  }
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+template <typename T>
+int upload(qasr_handle* h, T** dst, const std::vector<T>& src) {
+  void* p = nullptr;
+  QCUDA(h, cudaMalloc(&p, src.size() * sizeof(T)));
+  QCUDA(h, cudaMemcpy(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  h->weight_allocs.push_back(p);
+  h->stats.weight_bytes += src.size() * sizeof(T);
+  *dst = static_cast<T*>(p);
+  return QASR_OK;
+}
+int upload_bf16(qasr_handle* h, __nv_bfloat16** dst, const std::vector<float>& src) {
+  std::vector<uint16_t> tmp(src.size());
+  for (size_t i = 0; i < src.size(); ++i) tmp[i] = f32_to_bf16(src[i]);
+  uint16_t* p = nullptr;
+  int rc = upload<uint16_t>(h, &p, tmp);
+  *dst = reinterpret_cast<__nv_bfloat16*>(p);
+  return rc;
+}
+
+int init_mel_tables(qasr_handle* h) {
+  std::vector<float> win, fb;
+  std::vector<float2> tw;
+  build_hann_window_host(win);
+  build_twiddle_host(tw);
+  build_mel_filterbank_host(fb);
+  std::vector<int> start(kMelBins, 0), count(kMelBins, 0);
+  std::vector<float> wts(static_cast<size_t>(kMelBins) * kMelMaxTaps, 0.0f);
+  for (int m = 0; m < kMelBins; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < kMelFreqs; ++k)
+      if (fb[static_cast<size_t>(m) * kMelFreqs + k] != 0.0f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first < 0) continue;  // all-zero filter (rows 0,3,6,13 of the reference filterbank)
+    if (last - first + 1 > kMelMaxTaps) return fail(h, QASR_ERR_UNSUPPORTED, "mel filter wider than kMelMaxTaps");
+    start[m] = first;
+    count[m] = last - first + 1;
+    for (int j = 0; j < count[m]; ++j) wts[static_cast<size_t>(m) * kMelMaxTaps + j] = fb[static_cast<size_t>(m) * kMelFreqs + first + j];
+  }
+  int rc;
+  if ((rc = upload<float>(h, &h->d_window, win))) return rc;
+  if ((rc = upload<float2>(h, &h->d_twiddle, tw))) return rc;
+  if ((rc = upload<int>(h, &h->d_fb_start, start))) return rc;
+  if ((rc = upload<int>(h, &h->d_fb_count, count))) return rc;
+  if ((rc = upload<float>(h, &h->d_fb_weight, wts))) return rc;
+  QCUDA(h, cudaFuncSetAttribute(mel_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(MelSmem))));
+  return QASR_OK;
+}
+
+// SinusoidalPositionEmbedding (encoder.py:21-44), float32 arithmetic like the reference.
+void build_pe_host(int rows, int d_model, std::vector<float>& pe) {
+  const int half = d_model / 2;
+  const float log_timescale = static_cast<float>(log(10000.0) / (half - 1));
+  pe.assign(static_cast<size_t>(rows) * d_model, 0.0f);
+  for (int p = 0; p < rows; ++p)
+    for (int i = 0; i < half; ++i) {
+      const float inv = expf(-static_cast<float>(i) * log_timescale);
+      const float s = static_cast<float>(p) * inv;
+      pe[static_cast<size_t>(p) * d_model + i] = sinf(s);
+      pe[static_cast<size_t>(p) * d_model + half + i] = cosf(s);
+    }
+}
+
+int window_tokens(const qasr_config& c) { return kTokensPerChunk * (c.n_window_infer / kChunkFrames); }
+
+int validate_config(qasr_handle* h, const qasr_config& c) {
+  if (c.num_mel_bins != 128) return fail(h, QASR_ERR_UNSUPPORTED, "num_mel_bins must be 128");
+  if (c.n_window * 2 != kChunkFrames) return fail(h, QASR_ERR_UNSUPPORTED, "n_window must be 50 (100-frame chunks)");
+  if (c.downsample_hidden_size != kStemC) return fail(h, QASR_ERR_UNSUPPORTED, "downsample_hidden_size must be 480");
+  if (c.d_model < 128 || c.d_model > 1024 || c.d_model % 128 != 0)
+    return fail(h, QASR_ERR_UNSUPPORTED, "d_model must be a multiple of 128 in [128, 1024]");
+  if (c.encoder_attention_heads * 64 != c.d_model)
+    return fail(h, QASR_ERR_UNSUPPORTED, "head_dim (d_model / heads) must be 64");
+  if (c.encoder_ffn_dim < 64 || c.encoder_ffn_dim % 64 != 0)
+    return fail(h, QASR_ERR_UNSUPPORTED, "encoder_ffn_dim must be a multiple of 64");
+  if (c.output_dim < 32 || c.output_dim % 32 != 0) return fail(h, QASR_ERR_UNSUPPORTED, "output_dim must be a multiple of 32");
+  if (c.encoder_layers < 0 || c.encoder_layers > 256) return fail(h, QASR_ERR_INVALID, "bad encoder_layers");
+  if (c.n_window_infer < kChunkFrames || window_tokens(c) > 104)
+    return fail(h, QASR_ERR_UNSUPPORTED, "n_window_infer must be in [100, 800]");
+  if (c.max_source_positions < kTokensPerChunk) return fail(h, QASR_ERR_INVALID, "max_source_positions < 13");
+  return QASR_OK;
+}
+
+bool take(qasr_handle* h, const std::string& name, size_t expect, std::vector<float>& out, std::string& missing) {
+  auto it = h->staged.find(name);
+  if (it == h->staged.end() || it->second.size() != expect) {
+    missing = name + (it == h->staged.end() ? " (missing)" : " (wrong size)");
+    return false;
+  }
+  out.swap(it->second);
+  h->staged.erase(it);
+  return true;
+}
+
+int build_weight_maps(qasr_handle* h) {
+  const qasr_config& c = h->cfg;
+  std::string e;
+  const int D = c.d_model, F = c.encoder_ffn_dim;
+  if (!make_tmap_conv_w(&h->tm_conv2_w, h->conv2_w, kStemC, kStemC, 240, &e)) return fail(h, QASR_ERR_CUDA, e);
+  if (!make_tmap_conv_w(&h->tm_conv3_w, h->conv3_w, kStemC, kStemC, 240, &e)) return fail(h, QASR_ERR_CUDA, e);
+  if (!make_tmap_rows(&h->tm_convout_w, h->convout_w, D, 16 * kStemC, 16 * kStemC, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+  if (!make_tmap_rows(&h->tm_proj1_w, h->proj1_w, D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+  if (!make_tmap_rows(&h->tm_proj2_w, h->proj2_w, c.output_dim, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+  for (auto& L : h->layers) {
+    if (!make_tmap_rows(&L.tm_wqkv, L.wqkv, 3 * D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&L.tm_wo, L.wo, D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&L.tm_w1, L.w1, F, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&L.tm_w2, L.w2, D, F, F, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
+  }
+  return QASR_OK;
+}
+
+// Grow the workspace so that a call with `tokens`, `chunks`, `windows`, `batch` fits.
+int ensure_workspace(qasr_handle* h, long long tokens, long long chunks, long long windows, long long batch) {
+  const qasr_config& c = h->cfg;
+  const int D = c.d_model, F = c.encoder_ffn_dim;
+  int rc;
+  std::string e;
+  const long long group = chunks < h->stem_group ? chunks : h->stem_group;
+  if (group > h->cap_group) {
+    const long long G = group;
+    const size_t p1 = static_cast<size_t>(4) * G * 33 * 26 * kStemC * 2;
+    const size_t p2 = static_cast<size_t>(4) * G * 17 * 14 * kStemC * 2;
+    dev_free(h, h->planes1);
+    dev_free(h, h->planes2);
+    if ((rc = dev_alloc(h, h->planes1, p1, true))) return rc;  // zero borders are never written afterwards
+    if ((rc = dev_alloc(h, h->planes2, p2, true))) return rc;
+    if ((rc = dev_alloc(h, h->flat3, static_cast<size_t>(G) * 13 * 16 * kStemC * 2, true))) return rc;
+    if (!make_tmap_conv_act(&h->tm_planes1, h->planes1.p, kStemC, 26, G * 33, 25, 5, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_conv_act(&h->tm_planes2, h->planes2.p, kStemC, 14, G * 17, 13, 9, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&h->tm_flat3, h->flat3.p, G * 13, 16 * kStemC, 16 * kStemC, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    h->cap_group = G;
+  }
+  if (tokens > h->cap_tokens) {
+    const long long n = tokens;
+    const int wide = F > D ? F : D;
+    if ((rc = dev_alloc(h, h->x, static_cast<size_t>(n) * D * 4, false))) return rc;
+    if ((rc = dev_alloc(h, h->xn, static_cast<size_t>(n) * D * 2, true))) return rc;
+    if ((rc = dev_alloc(h, h->qkv, static_cast<size_t>(n) * 3 * D * 2, false))) return rc;
+    if ((rc = dev_alloc(h, h->attn, static_cast<size_t>(n) * D * 2, true))) return rc;
+    if ((rc = dev_alloc(h, h->hbuf, static_cast<size_t>(n) * wide * 2, true))) return rc;
+    if (!make_tmap_rows(&h->tm_xn, h->xn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&h->tm_attn, h->attn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&h->tm_h, h->hbuf.p, n, F, F, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&h->tm_p1, h->hbuf.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    h->cap_tokens = n;
+  }
+  if (chunks > h->cap_chunks) {
+    if ((rc = dev_alloc(h, h->d_chunks, static_cast<size_t>(chunks) * sizeof(ChunkDesc), false))) return rc;
+    if ((rc = dev_alloc(h, h->d_rowmap, static_cast<size_t>(chunks) * kTokensPerChunk * sizeof(int), false))) return rc;
+    h->cap_chunks = chunks;
+  }
+  if (windows > h->cap_windows) {
+    if ((rc = dev_alloc(h, h->d_windows, static_cast<size_t>(windows) * sizeof(WindowDesc), false))) return rc;
+    h->cap_windows = windows;
+  }
+  if (batch > h->cap_batch) {
+    if ((rc = dev_alloc(h, h->d_soffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
+    if ((rc = dev_alloc(h, h->d_foffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
+    if ((rc = dev_alloc(h, h->d_boffs, static_cast<size_t>(batch + 1) * 4, false))) return rc;
+    if ((rc = dev_alloc(h, h->d_uttmax, static_cast<size_t>(batch) * 4, false))) return rc;
+    h->cap_batch = batch;
+  }
+  return QASR_OK;
+}
+
+int ensure_pinned(qasr_handle* h, size_t bytes) {
+  if (h->pin_event_pending) {  // previous call's table upload must have drained before we overwrite
+    QCUDA(h, cudaEventSynchronize(h->pin_event));
+    h->pin_event_pending = false;
+  }
+  if (bytes <= h->pin_bytes) return QASR_OK;
+  if (h->pin) cudaFreeHost(h->pin);
+  h->pin = nullptr;
+  h->pin_bytes = 0;
+  QCUDA(h, cudaMallocHost(&h->pin, bytes));
+  h->pin_bytes = bytes;
+  return QASR_OK;
+}
+
+template <int VPL>
+void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
+  layernorm_bf16_kernel<VPL><<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, y, rows, 1e-5f);
+}
+int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
+  switch (h->cfg.d_model / 128) {
+    case 1: launch_ln<1>(x, g, b, y, rows, st); break;
+    case 2: launch_ln<2>(x, g, b, y, rows, st); break;
+    case 3: launch_ln<3>(x, g, b, y, rows, st); break;
+    case 4: launch_ln<4>(x, g, b, y, rows, st); break;
+    case 5: launch_ln<5>(x, g, b, y, rows, st); break;
+    case 6: launch_ln<6>(x, g, b, y, rows, st); break;
+    case 7: launch_ln<7>(x, g, b, y, rows, st); break;
+    case 8: launch_ln<8>(x, g, b, y, rows, st); break;
+    default: return fail(h, QASR_ERR_UNSUPPORTED, "d_model");
+  }
+  h->stats.kernel_launches++;
+  QCUDA(h, cudaGetLastError());
+  return QASR_OK;
+}
+
+template <int EPI>
+int dense(qasr_handle* h, const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, void* out, long long ldo,
+          const float* bias, cudaStream_t st) {
+  GemmParams p = dense_params(M, N, K, out, ldo, bias);
+  QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI>(ta, tw, p, st)));
+  h->stats.kernel_launches++;
+  return QASR_OK;
+}
+
+int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int B, float* mel_dev,
+             std::vector<long long>* frame_offsets_out, cudaStream_t st) {
+  if (!audio_dev || !sample_offsets || !mel_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_mel: bad argument");
+  std::vector<long long> soffs(B + 1), foffs(B + 1);
+  std::vector<int> boffs(B + 1);
+  soffs[0] = sample_offsets[0];
+  if (soffs[0] != 0) return fail(h, QASR_ERR_INVALID, "sample_offsets[0] must be 0");
+  foffs[0] = 0;
+  boffs[0] = 0;
+  for (int u = 0; u < B; ++u) {
+    const long long n = sample_offsets[u + 1] - sample_offsets[u];
+    if (n < kMelHop)
+      return fail(h, QASR_ERR_INVALID,
+                  "utterance " + std::to_string(u) + " has " + std::to_string(n) +
+                      " samples; need >= 160 (zero-size array to reduction operation maximum in the reference)");
+    const long long T = n / kMelHop;
+    soffs[u + 1] = sample_offsets[u + 1];
+    foffs[u + 1] = foffs[u] + T;
+    const long long nb = boffs[u] + (T + kMelFramesPerCta - 1) / kMelFramesPerCta;
+    if (nb > 0x7FFFFFFF) return fail(h, QASR_ERR_INVALID, "batch too large for one mel launch");
+    boffs[u + 1] = static_cast<int>(nb);
+  }
+  int rc;
+  if ((rc = ensure_workspace(h, 0, 0, 0, B))) return rc;
+  const size_t b8 = static_cast<size_t>(B + 1) * 8, b4 = static_cast<size_t>(B + 1) * 4;
+  if ((rc = ensure_pinned(h, 2 * b8 + b4))) return rc;
+  uint8_t* pin = static_cast<uint8_t*>(h->pin);
+  memcpy(pin, soffs.data(), b8);
+  memcpy(pin + b8, foffs.data(), b8);
+  memcpy(pin + 2 * b8, boffs.data(), b4);
+  QCUDA(h, cudaMemcpyAsync(h->d_soffs.p, pin, b8, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(h->d_foffs.p, pin + b8, b8, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(h->d_boffs.p, pin + 2 * b8, b4, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaEventRecord(h->pin_event, st));
+  h->pin_event_pending = true;
+  QCUDA(h, cudaMemsetAsync(h->d_uttmax.p, 0, static_cast<size_t>(B) * 4, st));
+
+  MelTables tab{h->d_window, h->d_twiddle, h->d_fb_start, h->d_fb_count, h->d_fb_weight};
+  mel_logmel_kernel<<<boffs[B], kMelThreads, sizeof(MelSmem), st>>>(
+      audio_dev, static_cast<const long long*>(h->d_soffs.p), static_cast<const long long*>(h->d_foffs.p),
+      static_cast<const int*>(h->d_boffs.p), B, tab, mel_dev, static_cast<unsigned*>(h->d_uttmax.p));
+  QCUDA(h, cudaGetLastError());
+  const long long total_vec4 = foffs[B] * (kMelBins / 4);
+  const long long nblk = (total_vec4 + kMelNormVecPerCta - 1) / kMelNormVecPerCta;
+  mel_normalize_kernel<<<static_cast<unsigned>(nblk), kMelNormThreads, 0, st>>>(
+      mel_dev, static_cast<const long long*>(h->d_foffs.p), B, static_cast<const unsigned*>(h->d_uttmax.p), total_vec4);
+  QCUDA(h, cudaGetLastError());
+  h->stats.kernel_launches += 2;
+  if (frame_offsets_out) *frame_offsets_out = foffs;
+  return QASR_OK;
+}
+
+int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
+                int out_dtype, int64_t* token_offsets_out, cudaStream_t st) {
+  if (!h->finalized) return fail(h, QASR_ERR_STATE, "weights not finalised (call qasr_finalize_weights)");
+  if (!mel_dev || !frame_offsets || !emb_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
+  if (frame_offsets[0] != 0) return fail(h, QASR_ERR_INVALID, "frame_offsets[0] must be 0");
+  const qasr_config& c = h->cfg;
+  const int D = c.d_model, F = c.encoder_ffn_dim, H = c.encoder_attention_heads;
+  const int wtok = window_tokens(c);
+
+  // ---- host-side bookkeeping: chunks, token packing map, attention windows (encoder.py:258-309)
+  std::vector<ChunkDesc> chunks;
+  std::vector<int> rowmap;
+  std::vector<WindowDesc> windows;
+  std::vector<long long> toffs(B + 1, 0);
+  for (int u = 0; u < B; ++u) {
+    const long long T = frame_offsets[u + 1] - frame_offsets[u];
+    if (T <= 0 || T > 0x7FFFFFF0LL) return fail(h, QASR_ERR_INVALID, "utterance with no mel frames");
+    const long long tok0 = toffs[u];
+    long long tok = tok0;
+    for (long long f0 = 0; f0 < T; f0 += kChunkFrames) {
+      const int real = static_cast<int>(T - f0 < kChunkFrames ? T - f0 : kChunkFrames);
+      const int valid = conv_len3(real);
+      chunks.push_back(ChunkDesc{static_cast<long long>(kMelBins) * frame_offsets[u], static_cast<int>(T), static_cast<int>(f0)});
+      for (int t = 0; t < kTokensPerChunk; ++t) rowmap.push_back(t < valid ? static_cast<int>(tok + t) : -1);
+      tok += valid;
+    }
+    if (tok > 0x7FFFFFF0LL) return fail(h, QASR_ERR_INVALID, "too many tokens for one call");
+    toffs[u + 1] = tok;
+    for (long long s = tok0; s < tok; s += wtok)
+      windows.push_back(WindowDesc{static_cast<int>(s), static_cast<int>(tok - s < wtok ? tok - s : wtok)});
+  }
+  const long long n = toffs[B];
+  const long long nchunks = static_cast<long long>(chunks.size());
+  const long long nwin = static_cast<long long>(windows.size());
+  if (token_offsets_out)
+    for (int u = 0; u <= B; ++u) token_offsets_out[u] = toffs[u];
+
+  int rc;
+  if ((rc = ensure_workspace(h, n, nchunks, nwin, B))) return rc;
+  const size_t bc = chunks.size() * sizeof(ChunkDesc), br = rowmap.size() * sizeof(int), bw = windows.size() * sizeof(WindowDesc);
+  if ((rc = ensure_pinned(h, bc + br + bw))) return rc;
+  uint8_t* pin = static_cast<uint8_t*>(h->pin);
+  memcpy(pin, chunks.data(), bc);
+  memcpy(pin + bc, rowmap.data(), br);
+  memcpy(pin + bc + br, windows.data(), bw);
+  QCUDA(h, cudaMemcpyAsync(h->d_chunks.p, pin, bc, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(h->d_rowmap.p, pin + bc, br, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(h->d_windows.p, pin + bc + br, bw, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaEventRecord(h->pin_event, st));
+  h->pin_event_pending = true;
+
+  float* x = static_cast<float*>(h->x.p);
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(h->xn.p);
+  __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(h->qkv.p);
+  __nv_bfloat16* attn = static_cast<__nv_bfloat16*>(h->attn.p);
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h->hbuf.p);
+
+  // ---- conv stem, in groups of chunks so that the activation planes stay bounded
+  const long long G = h->cap_group;
+  const long long ps1 = G * 33 * 26 * kStemC, ps2 = G * 17 * 14 * kStemC;
+  for (long long c0 = 0; c0 < nchunks; c0 += G) {
+    const int g = static_cast<int>(nchunks - c0 < G ? nchunks - c0 : G);
+    conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
+        mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
+        static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+    QCUDA(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
+      GemmParams p{};
+      p.M = g * 33 * 25; p.N = kStemC; p.K = 9 * kStemC;
+      p.conv_OW = 25; p.conv_OH = 32; p.conv_OHp = 33; p.conv_rows_per_tile = 5; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_chunks = g;
+      p.num_m_tiles = (g * 33 + 4) / 5;
+      p.num_k_blocks = 9 * p.conv_kc_per_tap;
+      p.out = h->planes2.p; p.bias = h->conv2_b;
+      p.out_Hp = 17; p.out_Wp = 14; p.out_plane_stride = ps2; p.out_C = kStemC;
+      QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES>(h->tm_planes1, h->tm_conv2_w, p, st)));
+      h->stats.kernel_launches++;
+    }
+    {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
+      GemmParams p{};
+      p.M = g * 17 * 13; p.N = kStemC; p.K = 9 * kStemC;
+      p.conv_OW = 13; p.conv_OH = 16; p.conv_OHp = 17; p.conv_rows_per_tile = 9; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_chunks = g;
+      p.num_m_tiles = (g * 17 + 8) / 9;
+      p.num_k_blocks = 9 * p.conv_kc_per_tap;
+      p.out = h->flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
+      QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT>(h->tm_planes2, h->tm_conv3_w, p, st)));
+      h->stats.kernel_launches++;
+    }
+    {  // conv_out + positional embedding + strip padding + pack (encoder.py:277-293)
+      GemmParams p = dense_params(g * kTokensPerChunk, D, 16 * kStemC, x, D, nullptr);
+      p.row_map = static_cast<const int*>(h->d_rowmap.p) + c0 * kTokensPerChunk;
+      p.pe = h->pe; p.pe_period = kTokensPerChunk;
+      QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK>(h->tm_flat3, h->tm_convout_w, p, st)));
+      h->stats.kernel_launches++;
+    }
+  }
+  if (h->debug) {
+    if ((rc = dev_alloc(h, h->dbg_stem, static_cast<size_t>(n) * D * 4, false))) return rc;
+    if ((rc = dev_alloc(h, h->dbg_layer0, static_cast<size_t>(n) * D * 4, false))) return rc;
+    if ((rc = dev_alloc(h, h->dbg_hidden, static_cast<size_t>(n) * D * 4, false))) return rc;
+    h->dbg_tokens = n;
+    QCUDA(h, cudaMemcpyAsync(h->dbg_stem.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
+  }
+
+  // ---- transformer layers (encoder.py:106-122)
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+  const int ni = static_cast<int>(n);
+  for (size_t li = 0; li < h->layers.size(); ++li) {
+    LayerWeights& L = h->layers[li];
+    if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, h->tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
+    window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
+        qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+    QCUDA(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    if ((rc = dense<EPI_RESID_F32>(h, h->tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
+    if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st))) return rc;
+    if ((rc = dense<EPI_GELU_BF16>(h, h->tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, h->tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
+    if (h->debug && li == 0)
+      QCUDA(h, cudaMemcpyAsync(h->dbg_layer0.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (h->debug) QCUDA(h, cudaMemcpyAsync(h->dbg_hidden.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- projector (encoder.py:319-321)
+  if ((rc = layernorm(h, x, h->lnp_g, h->lnp_b, xn, ni, st))) return rc;
+  if ((rc = dense<EPI_GELU_BF16>(h, h->tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
+  if (out_dtype == QASR_F32) {
+    if ((rc = dense<EPI_STORE_F32>(h, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+  } else {
+    if ((rc = dense<EPI_STORE_BF16>(h, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+  }
+  return QASR_OK;
+}
+
+int check_device(qasr_handle* h) {
+  QCUDA(h, cudaSetDevice(h->device));
+  return QASR_OK;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+void qasr_default_config(qasr_config* cfg) {
+  if (!cfg) return;
+  cfg->d_model = 1024; cfg->encoder_layers = 24; cfg->encoder_attention_heads = 16; cfg->encoder_ffn_dim = 4096;
+  cfg->num_mel_bins = 128; cfg->max_source_positions = 1500; cfg->output_dim = 2048; cfg->n_window = 50;
+  cfg->n_window_infer = 800; cfg->downsample_hidden_size = 480;
+}
+
+const char* qasr_last_error(const qasr_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
+  if (!cfg || !out) return fail(nullptr, QASR_ERR_INVALID, "qasr_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, QASR_ERR_UNSUPPORTED, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, QASR_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, QASR_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, QASR_ERR_UNSUPPORTED, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; libqasr is built for sm_100a only");
+  qasr_handle* h = new qasr_handle();
+  h->device = device;
+  h->cfg = *cfg;
+  int rc = validate_config(h, *cfg);
+  if (rc) { g_last_error = h->err; delete h; return rc; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaSetDevice failed"); }
+  if (const char* sg = getenv("QASR_STEM_GROUP")) {
+    const int v = atoi(sg);
+    if (v > 0) h->stem_group = v;
+  }
+  if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaEventCreate failed"); }
+  rc = init_mel_tables(h);
+  if (rc) { g_last_error = h->err; qasr_destroy(h); return rc; }
+  *out = h;
+  return QASR_OK;
+}
+
+void qasr_destroy(qasr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->weight_allocs) cudaFree(p);
+  DevBuf* bufs[] = {&h->planes1, &h->planes2, &h->flat3, &h->x, &h->xn, &h->qkv, &h->attn, &h->hbuf, &h->mel_scratch,
+                    &h->io_in, &h->io_out, &h->d_chunks, &h->d_rowmap, &h->d_windows, &h->d_soffs, &h->d_foffs,
+                    &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden};
+  for (DevBuf* b : bufs) dev_free(h, *b);
+  if (h->pin) cudaFreeHost(h->pin);
+  if (h->pin_event) cudaEventDestroy(h->pin_event);
+  delete h;
+}
+
+int qasr_set_weight(qasr_handle* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
+  if (!h || !name || !data || ndim < 1 || ndim > 4 || !shape) return fail(h, QASR_ERR_INVALID, "qasr_set_weight: bad argument");
+  if (h->finalized) return fail(h, QASR_ERR_STATE, "weights already finalised");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail(h, QASR_ERR_INVALID, "bad shape");
+    n *= static_cast<size_t>(shape[i]);
+  }
+  std::vector<float>& dst = h->staged[name];
+  dst.resize(n);
+  if (dtype == QASR_F32) memcpy(dst.data(), data, n * 4);
+  else if (dtype == QASR_BF16) {
+    const uint16_t* s = static_cast<const uint16_t*>(data);
+    for (size_t i = 0; i < n; ++i) dst[i] = bf16_to_f32(s[i]);
+  } else return fail(h, QASR_ERR_INVALID, "bad dtype");
+  return QASR_OK;
+}
+
+int qasr_finalize_weights(qasr_handle* h) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  if (h->finalized) return QASR_OK;
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const qasr_config& c = h->cfg;
+  const size_t D = c.d_model, F = c.encoder_ffn_dim, C = kStemC, O = c.output_dim;
+  std::string miss;
+  std::vector<float> w, b, g;
+#define TAKE(name, count, vec) \
+  if (!take(h, name, count, vec, miss)) return fail(h, QASR_ERR_STATE, "parameter " + miss)
+  TAKE("conv2d1.weight", C * 9, w); TAKE("conv2d1.bias", C, b);
+  if ((rc = upload<float>(h, &h->conv1_w, w)) || (rc = upload<float>(h, &h->conv1_b, b))) return rc;
+  TAKE("conv2d2.weight", C * 9 * C, w); TAKE("conv2d2.bias", C, b);
+  if ((rc = upload_bf16(h, &h->conv2_w, w)) || (rc = upload<float>(h, &h->conv2_b, b))) return rc;
+  TAKE("conv2d3.weight", C * 9 * C, w); TAKE("conv2d3.bias", C, b);
+  if ((rc = upload_bf16(h, &h->conv3_w, w)) || (rc = upload<float>(h, &h->conv3_b, b))) return rc;
+  TAKE("conv_out.weight", D * 16 * C, w);
+  {  // reference flat index = channel*16 + freq (encoder.py:277-278); ours = freq*480 + channel
+    std::vector<float> perm(w.size());
+    for (size_t n = 0; n < D; ++n)
+      for (size_t ch = 0; ch < C; ++ch)
+        for (size_t f = 0; f < 16; ++f) perm[n * 16 * C + f * C + ch] = w[n * 16 * C + ch * 16 + f];
+    if ((rc = upload_bf16(h, &h->convout_w, perm))) return rc;
+  }
+  h->layers.resize(c.encoder_layers);
+  for (int i = 0; i < c.encoder_layers; ++i) {
+    LayerWeights& L = h->layers[i];
+    const std::string p = "layers." + std::to_string(i) + ".";
+    std::vector<float> wq, wk, wv, bq, bk, bv;
+    TAKE(p + "self_attn.q_proj.weight", D * D, wq); TAKE(p + "self_attn.k_proj.weight", D * D, wk);
+    TAKE(p + "self_attn.v_proj.weight", D * D, wv);
+    TAKE(p + "self_attn.q_proj.bias", D, bq); TAKE(p + "self_attn.k_proj.bias", D, bk); TAKE(p + "self_attn.v_proj.bias", D, bv);
+    wq.insert(wq.end(), wk.begin(), wk.end()); wq.insert(wq.end(), wv.begin(), wv.end());
+    bq.insert(bq.end(), bk.begin(), bk.end()); bq.insert(bq.end(), bv.begin(), bv.end());
+    if ((rc = upload_bf16(h, &L.wqkv, wq)) || (rc = upload<float>(h, &L.bqkv, bq))) return rc;
+    TAKE(p + "self_attn.out_proj.weight", D * D, w); TAKE(p + "self_attn.out_proj.bias", D, b);
+    if ((rc = upload_bf16(h, &L.wo, w)) || (rc = upload<float>(h, &L.bo, b))) return rc;
+    TAKE(p + "fc1.weight", F * D, w); TAKE(p + "fc1.bias", F, b);
+    if ((rc = upload_bf16(h, &L.w1, w)) || (rc = upload<float>(h, &L.b1, b))) return rc;
+    TAKE(p + "fc2.weight", D * F, w); TAKE(p + "fc2.bias", D, b);
+    if ((rc = upload_bf16(h, &L.w2, w)) || (rc = upload<float>(h, &L.b2, b))) return rc;
+    TAKE(p + "self_attn_layer_norm.weight", D, g); TAKE(p + "self_attn_layer_norm.bias", D, b);
+    if ((rc = upload<float>(h, &L.ln1g, g)) || (rc = upload<float>(h, &L.ln1b, b))) return rc;
+    TAKE(p + "final_layer_norm.weight", D, g); TAKE(p + "final_layer_norm.bias", D, b);
+    if ((rc = upload<float>(h, &L.ln2g, g)) || (rc = upload<float>(h, &L.ln2b, b))) return rc;
+  }
+  TAKE("ln_post.weight", D, g); TAKE("ln_post.bias", D, b);
+  if ((rc = upload<float>(h, &h->lnp_g, g)) || (rc = upload<float>(h, &h->lnp_b, b))) return rc;
+  TAKE("proj1.weight", D * D, w); TAKE("proj1.bias", D, b);
+  if ((rc = upload_bf16(h, &h->proj1_w, w)) || (rc = upload<float>(h, &h->proj1_b, b))) return rc;
+  TAKE("proj2.weight", O * D, w); TAKE("proj2.bias", O, b);
+  if ((rc = upload_bf16(h, &h->proj2_w, w)) || (rc = upload<float>(h, &h->proj2_b, b))) return rc;
+#undef TAKE
+  if (!h->staged.empty()) return fail(h, QASR_ERR_INVALID, "unexpected parameter " + h->staged.begin()->first);
+  std::vector<float> pe;
+  build_pe_host(kTokensPerChunk, c.d_model, pe);
+  if ((rc = upload<float>(h, &h->pe, pe))) return rc;
+  if ((rc = build_weight_maps(h))) return rc;
+  h->finalized = true;
+  return QASR_OK;
+}
+
+int qasr_count_frames(int64_t n_samples, int64_t* n_frames) {
+  if (!n_frames) return fail(nullptr, QASR_ERR_INVALID, "null output");
+  if (n_samples < kMelHop) return fail(nullptr, QASR_ERR_INVALID, "need >= 160 samples");
+  *n_frames = n_samples / kMelHop;
+  return QASR_OK;
+}
+
+int qasr_count_tokens(const qasr_handle* h, int64_t n_frames, int64_t* n_tokens) {
+  (void)h;
+  if (!n_tokens || n_frames <= 0) return fail(nullptr, QASR_ERR_INVALID, "qasr_count_tokens: bad argument");
+  const int64_t full = n_frames / kChunkFrames, rem = n_frames % kChunkFrames;
+  *n_tokens = full * kTokensPerChunk + (rem ? conv_len3(static_cast<int>(rem)) : 0);
+  return QASR_OK;
+}
+
+int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch) {
+  if (!h || total_frames <= 0 || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_reserve: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const long long chunks = total_frames / kChunkFrames + batch;
+  const long long tokens = chunks * kTokensPerChunk;
+  const long long windows = tokens / window_tokens(h->cfg) + batch;
+  if ((rc = ensure_workspace(h, tokens, chunks, windows, batch))) return rc;
+  if (total_frames > h->cap_mel_frames) {
+    if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(total_frames) * kMelBins * 4, false))) return rc;
+    h->cap_mel_frames = total_frames;
+  }
+  return QASR_OK;
+}
+
+int qasr_mel(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, float* mel_dev, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  return mel_impl(h, audio_dev, sample_offsets, batch, mel_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int qasr_encode(qasr_handle* h, const float* mel_dev, const int64_t* frame_offsets, int32_t batch, void* emb_dev,
+                int out_dtype, int64_t* token_offsets_out, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  if (!frame_offsets || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
+  std::vector<long long> fo(frame_offsets, frame_offsets + batch + 1);
+  return encode_impl(h, mel_dev, fo.data(), batch, emb_dev, out_dtype, token_offsets_out, static_cast<cudaStream_t>(stream));
+}
+
+int qasr_encode_audio(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, void* emb_dev,
+                      int out_dtype, int64_t* token_offsets_out, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  if (!sample_offsets || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_audio: bad argument");
+  long long total_frames = 0;
+  for (int u = 0; u < batch; ++u) total_frames += (sample_offsets[u + 1] - sample_offsets[u]) / kMelHop;
+  if (total_frames <= 0) return fail(h, QASR_ERR_INVALID, "no frames");
+  if (total_frames > h->cap_mel_frames) {
+    if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(total_frames) * kMelBins * 4, false))) return rc;
+    h->cap_mel_frames = total_frames;
+  }
+  std::vector<long long> foffs;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = mel_impl(h, audio_dev, sample_offsets, batch, static_cast<float*>(h->mel_scratch.p), &foffs, st))) return rc;
+  return encode_impl(h, static_cast<const float*>(h->mel_scratch.p), foffs.data(), batch, emb_dev, out_dtype, token_offsets_out, st);
+}
+
+int qasr_mel_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch, float* mel_host) {
+  if (!h || !audio_host || !sample_offsets || !mel_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_mel_host: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const long long ns = sample_offsets[batch];
+  long long nf = 0;
+  for (int u = 0; u < batch; ++u) nf += (sample_offsets[u + 1] - sample_offsets[u]) / kMelHop;
+  if (ns <= 0 || nf <= 0) return fail(h, QASR_ERR_INVALID, "need >= 160 samples per utterance");
+  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(ns) * 4, false))) return rc;
+  if ((rc = dev_alloc(h, h->io_out, static_cast<size_t>(nf) * kMelBins * 4, false))) return rc;
+  QCUDA(h, cudaMemcpyAsync(h->io_in.p, audio_host, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, 0));
+  if ((rc = mel_impl(h, static_cast<const float*>(h->io_in.p), sample_offsets, batch, static_cast<float*>(h->io_out.p), nullptr, 0))) return rc;
+  QCUDA(h, cudaMemcpyAsync(mel_host, h->io_out.p, static_cast<size_t>(nf) * kMelBins * 4, cudaMemcpyDeviceToHost, 0));
+  QCUDA(h, cudaStreamSynchronize(0));
+  return QASR_OK;
+}
+
+int qasr_encode_host(qasr_handle* h, const float* mel_host, const int64_t* frame_offsets, int32_t batch, void* emb_host,
+                     int out_dtype, int64_t* token_offsets_out) {
+  if (!h || !mel_host || !frame_offsets || !emb_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_host: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const long long nf = frame_offsets[batch];
+  if (nf <= 0) return fail(h, QASR_ERR_INVALID, "no frames");
+  long long ntok = 0;
+  for (int u = 0; u < batch; ++u) {
+    int64_t t = 0;
+    if (frame_offsets[u + 1] - frame_offsets[u] <= 0) return fail(h, QASR_ERR_INVALID, "utterance with no mel frames");
+    qasr_count_tokens(h, frame_offsets[u + 1] - frame_offsets[u], &t);
+    ntok += t;
+  }
+  const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
+  const size_t out_bytes = static_cast<size_t>(ntok) * h->cfg.output_dim * esz;
+  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(nf) * kMelBins * 4, false))) return rc;
+  if ((rc = dev_alloc(h, h->io_out, out_bytes, false))) return rc;
+  QCUDA(h, cudaMemcpyAsync(h->io_in.p, mel_host, static_cast<size_t>(nf) * kMelBins * 4, cudaMemcpyHostToDevice, 0));
+  std::vector<long long> fo(frame_offsets, frame_offsets + batch + 1);
+  if ((rc = encode_impl(h, static_cast<const float*>(h->io_in.p), fo.data(), batch, h->io_out.p, out_dtype, token_offsets_out, 0))) return rc;
+  QCUDA(h, cudaMemcpyAsync(emb_host, h->io_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+  QCUDA(h, cudaStreamSynchronize(0));
+  return QASR_OK;
+}
+
+int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
+                           void* emb_host, int out_dtype, int64_t* token_offsets_out) {
+  if (!h || !audio_host || !sample_offsets || !emb_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_audio_host: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const long long ns = sample_offsets[batch];
+  long long ntok = 0;
+  for (int u = 0; u < batch; ++u) {
+    const long long n = sample_offsets[u + 1] - sample_offsets[u];
+    if (n < kMelHop) return fail(h, QASR_ERR_INVALID, "need >= 160 samples per utterance");
+    int64_t t = 0;
+    qasr_count_tokens(h, n / kMelHop, &t);
+    ntok += t;
+  }
+  const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
+  const size_t out_bytes = static_cast<size_t>(ntok) * h->cfg.output_dim * esz;
+  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(ns) * 4, false))) return rc;
+  if ((rc = dev_alloc(h, h->io_out, out_bytes, false))) return rc;
+  QCUDA(h, cudaMemcpyAsync(h->io_in.p, audio_host, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, 0));
+  if ((rc = qasr_encode_audio(h, static_cast<const float*>(h->io_in.p), sample_offsets, batch, h->io_out.p, out_dtype, token_offsets_out, nullptr))) return rc;
+  QCUDA(h, cudaMemcpyAsync(emb_host, h->io_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+  QCUDA(h, cudaStreamSynchronize(0));
+  return QASR_OK;
+}
+
+int qasr_mel_filterbank(float* out) {
+  if (!out) return fail(nullptr, QASR_ERR_INVALID, "null output");
+  std::vector<float> fb;
+  build_mel_filterbank_host(fb);
+  memcpy(out, fb.data(), fb.size() * 4);
+  return QASR_OK;
+}
+int qasr_hann_window(float* out) {
+  if (!out) return fail(nullptr, QASR_ERR_INVALID, "null output");
+  std::vector<float> w;
+  build_hann_window_host(w);
+  memcpy(out, w.data(), w.size() * 4);
+  return QASR_OK;
+}
+int qasr_positional_embedding(const qasr_handle* h, int32_t rows, float* out) {
+  if (!h || !out || rows <= 0 || rows > h->cfg.max_source_positions) return fail(nullptr, QASR_ERR_INVALID, "qasr_positional_embedding: bad argument");
+  std::vector<float> pe;
+  build_pe_host(rows, h->cfg.d_model, pe);
+  memcpy(out, pe.data(), pe.size() * 4);
+  return QASR_OK;
+}
+
+int qasr_get_stats(const qasr_handle* h, qasr_stats* out) {
+  if (!h || !out) return fail(nullptr, QASR_ERR_INVALID, "null argument");
+  *out = h->stats;
+  return QASR_OK;
+}
+
+int qasr_set_debug(qasr_handle* h, int enabled) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  h->debug = enabled != 0;
+  return QASR_OK;
+}
+
+int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_floats) {
+  if (!h || !what || !host_out) return fail(h, QASR_ERR_INVALID, "qasr_debug_read: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  DevBuf* b = nullptr;
+  if (!strcmp(what, "stem")) b = &h->dbg_stem;
+  else if (!strcmp(what, "layer0")) b = &h->dbg_layer0;
+  else if (!strcmp(what, "hidden")) b = &h->dbg_hidden;
+  if (!b || !b->p) return fail(h, QASR_ERR_STATE, "no such debug buffer (enable qasr_set_debug before encoding)");
+  const size_t have = static_cast<size_t>(h->dbg_tokens) * h->cfg.d_model;
+  if (n_floats > have) return fail(h, QASR_ERR_INVALID, "debug buffer smaller than requested");
+  QCUDA(h, cudaDeviceSynchronize());
+  QCUDA(h, cudaMemcpy(host_out, b->p, n_floats * 4, cudaMemcpyDeviceToHost));
+  return QASR_OK;
+}
+
+int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float* bias, int32_t M, int32_t N, int32_t K,
+                   int32_t mode, float* out) {
+  if (!a || !w || !out || M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0)
+    return fail(nullptr, QASR_ERR_INVALID, "qasr_test_gemm: bad argument (need N % 32 == 0, K % 8 == 0)");
+  qasr_handle* h = nullptr;
+  QCUDA(h, cudaSetDevice(device));
+  void *da = nullptr, *dw = nullptr, *db = nullptr, *dout = nullptr;
+  QCUDA(h, cudaMalloc(&da, static_cast<size_t>(M) * K * 2));
+  QCUDA(h, cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
+  QCUDA(h, cudaMalloc(&dout, static_cast<size_t>(M) * N * 4));
+  QCUDA(h, cudaMemcpy(da, a, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
+  QCUDA(h, cudaMemcpy(dw, w, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
+  if (bias) {
+    QCUDA(h, cudaMalloc(&db, static_cast<size_t>(N) * 4));
+    QCUDA(h, cudaMemcpy(db, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice));
+  }
+  CUtensorMap ta, tw;
+  std::string e;
+  if (!make_tmap_rows(&ta, da, M, K, K, kBlockM, &e) || !make_tmap_rows(&tw, dw, N, K, K, 256, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
+  GemmParams p = dense_params(M, N, K, dout, N, static_cast<const float*>(db));
+  if (mode == 1) QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_GELU_F32>(ta, tw, p, 0)));
+  else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_STORE_F32>(ta, tw, p, 0)));
+  QCUDA(h, cudaDeviceSynchronize());
+  QCUDA(h, cudaMemcpy(out, dout, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(dw); cudaFree(dout);
+  if (db) cudaFree(db);
+  return QASR_OK;
+}
+
+}  // extern "C"
