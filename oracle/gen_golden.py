@@ -1,0 +1,69 @@
+"""Generate tests/golden/* (run in the authoring container, where /root/reference exists).
+
+mel_*.npz     : inputs and outputs of the REFERENCE's own log_mel_spectrogram executed verbatim
+                (oracle/mel_ref.py) -> these pin oracle/mel_np.py and the CUDA mel kernels.
+mel_filterbank.npy : the reference's _get_mel_filterbank().
+encoder_small.npz  : oracle/encoder_np.py (fp64) output for a small seeded configuration.  NOT
+                reference-pinned (MLX cannot run here); a drift anchor for the two restatements.
+
+    python oracle/gen_golden.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import encoder_np, mel_np, mel_ref  # noqa: E402
+from qwen3_asr_mlx_b200 import weights  # noqa: E402
+from qwen3_asr_mlx_b200.config import AudioEncoderConfig  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def synth(rng, n):
+    """SURVEY.md §8d recipe: 0.1*N(0,1) + 3 tones (100-4000 Hz, amp 0.3) x slow envelope, clipped."""
+    t = np.arange(n) / 16000.0
+    x = 0.1 * rng.standard_normal(n)
+    for _ in range(3):
+        x += 0.3 * np.sin(2 * np.pi * rng.uniform(100, 4000) * t + rng.uniform(0, 6.28)) * (0.5 + 0.5 * np.sin(2 * np.pi * rng.uniform(0.1, 1.0) * t))
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    assert mel_ref.available(), "needs /root/reference"
+    rng = np.random.default_rng(20261018)
+    cases = {}
+    for n in (160, 161, 199, 200, 201, 319, 400, 2417, 16000):
+        cases[f"noise_{n}"] = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    cases["silence_16000"] = np.zeros(16000, dtype=np.float32)
+    t = np.linspace(0.0, 1.0, 16000, endpoint=False)
+    cases["tone440_16000"] = np.sin(2.0 * np.pi * 440.0 * t).astype(np.float32)
+    cases["synth_48000"] = synth(rng, 48000)
+    cases["synth_quiet_24000"] = (1e-3 * synth(rng, 24000)).astype(np.float32)
+    out = {}
+    for name, x in cases.items():
+        out["in_" + name] = x
+        out["out_" + name] = np.asarray(mel_ref.log_mel_spectrogram(x), dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLDEN, "mel_reference.npz"), **out)
+    np.save(os.path.join(GOLDEN, "mel_filterbank.npy"), np.asarray(mel_ref.mel_filterbank(), dtype=np.float32))
+
+    cfg = AudioEncoderConfig(d_model=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_dim=512, output_dim=256)
+    P = weights.random_init(cfg, seed=7, exercise_all=True)
+    x = synth(np.random.default_rng(7), 16000 * 9 + 4321)  # 927 frames: 9 full chunks + 27 frames -> 117 + 4 = 121 tokens, 2 windows
+    mel = mel_np.log_mel_spectrogram(x)
+    emb = encoder_np.encoder_forward(P, cfg, mel)
+    np.savez_compressed(os.path.join(GOLDEN, "encoder_small.npz"), audio=x, emb=emb.astype(np.float32),
+                        cfg=np.array([cfg.d_model, cfg.encoder_layers, cfg.encoder_attention_heads, cfg.encoder_ffn_dim, cfg.output_dim]),
+                        seed=np.array(7))
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,7 @@ struct GemmParams {
   int conv_rows_per_tile;  // output rows per M tile (rows_per_tile * OW <= 128)
   int conv_kc_per_tap;     // K blocks per filter tap (ceil(C / 64))
   int conv_chunks;         // number of real chunks
+  int a_tx_bytes;          // bytes one A-operand TMA box delivers (0 -> full stage: 128 rows x 128 B)
   // EPI_CONV_PLANES destination geometry
   int out_Hp, out_Wp;             // padded rows per chunk / padded width of destination planes
   long long out_plane_stride;     // elements between destination planes
@@ -182,12 +183,14 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // a conv box covers rows_per_tile * OW (< 128) pixels: the tail rows of the stage are never written
+      const uint32_t a_tx = p.a_tx_bytes > 0 ? static_cast<uint32_t>(p.a_tx_bytes) : static_cast<uint32_t>(L::kABytes);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::mbar_expect_tx(&full_bar[stage], a_tx + L::kBBytes);
           void* sa = smem_a + stage * L::kABytes;
           void* sb = smem_b + stage * L::kBBytes;
           if constexpr (kAMode == A_ROWS) {

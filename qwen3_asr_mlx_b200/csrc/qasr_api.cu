@@ -478,7 +478,7 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
       GemmParams p{};
       p.M = g * 33 * 25; p.N = kStemC; p.K = 9 * kStemC;
-      p.conv_OW = 25; p.conv_OH = 32; p.conv_OHp = 33; p.conv_rows_per_tile = 5; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_OW = 25; p.conv_OH = 32; p.conv_OHp = 33; p.conv_rows_per_tile = 5; p.a_tx_bytes = 5 * 25 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
       p.conv_chunks = g;
       p.num_m_tiles = (g * 33 + 4) / 5;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
@@ -490,7 +490,7 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
     {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
       GemmParams p{};
       p.M = g * 17 * 13; p.N = kStemC; p.K = 9 * kStemC;
-      p.conv_OW = 13; p.conv_OH = 16; p.conv_OHp = 17; p.conv_rows_per_tile = 9; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_OW = 13; p.conv_OH = 16; p.conv_OHp = 17; p.conv_rows_per_tile = 9; p.a_tx_bytes = 9 * 13 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
       p.conv_chunks = g;
       p.num_m_tiles = (g * 17 + 8) / 9;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;

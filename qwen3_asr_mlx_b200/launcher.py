@@ -1,0 +1,125 @@
+"""Data-parallel launcher: shard utterance batches over the GPUs of one box.
+
+One process per GPU (torchrun), weights replicated, NO collective on the forward path; the
+only communication is the final gather of embeddings.  Utterances are
+assigned to ranks by longest-processing-time-first over their token counts so that every
+rank encodes about the same number of tokens.  The reference has no counterpart (it handles
+one utterance at a time under a lock, model.py:145,239); results are defined as equal to a
+per-utterance loop over the reference.
+"""
+from __future__ import annotations
+
+import heapq
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CHUNK_FRAMES = 100
+TOKENS_PER_CHUNK = 13
+HOP = 160
+
+
+def conv_output_length(n: int) -> int:
+    for _ in range(3):
+        n = (n - 1) // 2 + 1
+    return n
+
+
+def tokens_for_samples(n_samples: int) -> int:
+    """Audio tokens the encoder emits for an utterance of ``n_samples`` (encoder.py:258-293)."""
+    frames = n_samples // HOP
+    full, rem = divmod(frames, CHUNK_FRAMES)
+    return full * TOKENS_PER_CHUNK + (conv_output_length(rem) if rem else 0)
+
+
+def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Greedy LPT: heaviest item first onto the currently lightest rank.  Deterministic
+    (ties broken by index / rank), so every rank computes the same assignment locally."""
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    heap = [(0, r) for r in range(world_size)]
+    heapq.heapify(heap)
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        parts[r].append(i)
+        heapq.heappush(heap, (load + int(costs[i]), r))
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def split_by_budget(indices: Sequence[int], costs: Sequence[int], budget: int) -> List[List[int]]:
+    """Split one rank's share into consecutive sub-batches of at most ``budget`` tokens each
+    (bounds the activation workspace of one libqasr call)."""
+    out: List[List[int]] = []
+    cur: List[int] = []
+    acc = 0
+    for i in indices:
+        c = int(costs[i])
+        if cur and acc + c > budget:
+            out.append(cur)
+            cur, acc = [], 0
+        cur.append(i)
+        acc += c
+    if cur:
+        out.append(cur)
+    return out
+
+
+EncodeFn = Callable[[List[int]], Tuple[torch.Tensor, np.ndarray]]
+
+
+def encode_sharded(encode_fn: EncodeFn, n_samples: Sequence[int], output_dim: int, rank: int, world_size: int,
+                   tokens_per_call: int = 32768, gather: bool = True, group=None,
+                   dtype: torch.dtype = torch.float32) -> Tuple[Optional[torch.Tensor], np.ndarray, List[int]]:
+    """Encode utterances ``0..len(n_samples)-1`` data-parallel.
+
+    ``encode_fn(indices)`` must return ``(embeddings (sum tokens, output_dim), token_offsets)`` for
+    the utterances ``indices`` (in that order) on this rank's device.  Returns
+    ``(all_embeddings or None, token_offsets (B+1,), my_indices)``: with ``gather=True`` every rank
+    receives the embeddings of ALL utterances in original order.
+    """
+    costs = [tokens_for_samples(int(n)) for n in n_samples]
+    parts = lpt_partition(costs, world_size)
+    mine = parts[rank]
+    pieces: List[torch.Tensor] = []
+    for sub in split_by_budget(mine, costs, tokens_per_call):
+        emb, toffs = encode_fn(sub)
+        assert int(toffs[-1]) == sum(costs[i] for i in sub), "token count mismatch between host rule and library"
+        pieces.append(emb)
+    global_offsets = np.zeros(len(costs) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(costs, dtype=np.int64), out=global_offsets[1:])
+    if not gather:
+        local = torch.cat(pieces) if pieces else None
+        return local, global_offsets, mine
+    device = pieces[0].device if pieces else torch.device("cpu")
+    local = torch.cat(pieces) if pieces else torch.zeros((0, output_dim), dtype=dtype, device=device)
+    return gather_embeddings(local, parts, costs, output_dim, rank, world_size, group), global_offsets, mine
+
+
+def gather_embeddings(local: torch.Tensor, parts: List[List[int]], costs: Sequence[int], output_dim: int, rank: int,
+                      world_size: int, group=None) -> torch.Tensor:
+    """Final gather (all-gather-v on a max-padded buffer) + restore of the original utterance order."""
+    per_rank = [sum(int(costs[i]) for i in p) for p in parts]
+    total = sum(per_rank)
+    if world_size == 1:
+        gathered = [local]
+    else:
+        pad = max(per_rank)
+        buf = torch.zeros((pad, output_dim), dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]].copy_(local)
+        out = torch.empty((world_size * pad, output_dim), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        gathered = [out[r * pad: r * pad + per_rank[r]] for r in range(world_size)]
+    result = torch.empty((total, output_dim), dtype=local.dtype, device=local.device)
+    offsets = np.zeros(len(costs) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(costs, dtype=np.int64), out=offsets[1:])
+    for r, p in enumerate(parts):
+        pos = 0
+        for i in p:
+            n = int(costs[i])
+            result[int(offsets[i]): int(offsets[i]) + n].copy_(gathered[r][pos: pos + n])
+            pos += n
+    return result

@@ -1,0 +1,86 @@
+"""CPU: the mel oracle against the reference's golden vectors and known-answer tests
+(reference tests/test_audio.py:35-126)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mel_np, mel_ref
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "mel_reference.npz"))
+
+
+def test_oracle_matches_reference_golden_bit_exact(golden):
+    names = [k[3:] for k in golden.files if k.startswith("in_")]
+    assert len(names) >= 12
+    for name in names:
+        got = mel_np.log_mel_spectrogram(golden["in_" + name])
+        ref = golden["out_" + name]
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert np.array_equal(got, ref), f"{name}: max diff {np.abs(got - ref).max()}"
+
+
+def test_fast_variant_equals_loop(golden):
+    for name in ("noise_2417", "synth_48000", "noise_160", "noise_199"):
+        x = golden["in_" + name]
+        assert np.array_equal(mel_np.log_mel_spectrogram_fast(x), mel_np.log_mel_spectrogram(x))
+
+
+def test_filterbank_matches_reference(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "mel_filterbank.npy"))
+    fb = mel_np.mel_filterbank()
+    assert fb.shape == (128, 201) and fb.dtype == np.float32
+    assert np.array_equal(fb, ref)
+    assert (fb >= 0).all()
+    # 395 non-zeros, <= 9 per row, rows 0,3,6,13 empty, DC column unused
+    assert int((fb != 0).sum()) == 395
+    assert int((fb != 0).sum(axis=1).max()) <= 9
+    assert [i for i in range(128) if not fb[i].any()] == [0, 3, 6, 13]
+    assert not fb[:, 0].any()
+
+
+def test_silence_known_answer():
+    # reference tests/test_audio.py:80-89: every value == -1.5 (atol 1e-3)
+    mel = mel_np.log_mel_spectrogram(np.zeros(16000, dtype=np.float32))
+    assert mel.shape == (128, 100)
+    assert np.allclose(mel, -1.5, atol=1e-3)
+
+
+def test_frame_count_rule():
+    # reference tests/test_audio.py:49-63: T = N // 160
+    for n in (160, 8000, 16000, 32000, 80000, 16000 * 3 + 159):
+        assert mel_np.log_mel_spectrogram_fast(np.zeros(n, dtype=np.float32)).shape == (128, n // 160)
+
+
+def test_tone_value_range():
+    t = np.linspace(0.0, 1.0, 16000, endpoint=False)
+    mel = mel_np.log_mel_spectrogram(np.sin(2 * np.pi * 440 * t).astype(np.float32))
+    assert mel.max() < 10.0 and mel.min() > -5.0
+
+
+def test_too_short_raises():
+    with pytest.raises(ValueError):
+        mel_np.log_mel_spectrogram(np.zeros(159, dtype=np.float32))
+
+
+@pytest.mark.skipif(not mel_ref.available(), reason="reference tree not present (GPU box)")
+def test_oracle_equals_reference_run_verbatim():
+    rng = np.random.default_rng(5)
+    for n in (160, 777, 12345, 40000):
+        x = (0.2 * rng.standard_normal(n)).astype(np.float32)
+        assert np.array_equal(mel_np.log_mel_spectrogram(x), np.asarray(mel_ref.log_mel_spectrogram(x)))
+
+
+def test_package_filterbank_helpers(golden_dir):
+    # host-side table builders kept for interface parity (reference tests/test_audio.py:102-126)
+    from qwen3_asr_mlx_b200 import audio
+
+    audio._mel_filterbank_cache.clear()
+    fb1 = audio._get_mel_filterbank()
+    fb2 = audio._get_mel_filterbank()
+    assert fb1 is fb2 and len(audio._mel_filterbank_cache) == 1
+    assert fb1.shape == (audio.N_MELS, audio.N_FFT // 2 + 1)
+    assert np.array_equal(fb1, np.load(os.path.join(golden_dir, "mel_filterbank.npy")))
