@@ -67,6 +67,19 @@ typedef struct {
   uint64_t weight_bytes;
 } qasr_stats;
 
+/* Per-kernel-category timing, measured with CUDA events recorded on the launch stream. */
+enum {
+  QASR_PROF_MEL_LOGMEL = 0, QASR_PROF_MEL_NORM, QASR_PROF_CONV1, QASR_PROF_CONV2, QASR_PROF_CONV3, QASR_PROF_CONV_OUT,
+  QASR_PROF_LAYERNORM, QASR_PROF_GEMM_QKV, QASR_PROF_ATTENTION, QASR_PROF_GEMM_OPROJ, QASR_PROF_GEMM_FC1,
+  QASR_PROF_GEMM_FC2, QASR_PROF_GEMM_PROJ, QASR_PROF_CATEGORIES
+};
+typedef struct {
+  double ms[QASR_PROF_CATEGORIES];         /* summed device time of the category's launches */
+  double flops[QASR_PROF_CATEGORIES];      /* ALGORITHMIC flops of those launches (SURVEY.md 8d counting) */
+  double bytes[QASR_PROF_CATEGORIES];      /* ALGORITHMIC bytes (memory-bound categories) */
+  uint64_t launches[QASR_PROF_CATEGORIES];
+} qasr_profile;
+
 void qasr_default_config(qasr_config* cfg);
 
 int qasr_create(int device, const qasr_config* cfg, qasr_handle** out);
@@ -112,6 +125,12 @@ int qasr_hann_window(float* out_400);
 int qasr_positional_embedding(const qasr_handle* h, int32_t rows, float* out_rows_x_dmodel);
 
 int qasr_get_stats(const qasr_handle* h, qasr_stats* out);
+
+/* Enable/disable event bracketing of every launch (resets the accumulators). */
+int qasr_set_profile(qasr_handle* h, int enabled);
+/* Synchronises the device and returns the totals accumulated since qasr_set_profile. */
+int qasr_get_profile(qasr_handle* h, qasr_profile* out);
+const char* qasr_profile_name(int category);
 
 /* ---- test hooks ---- */
 /* When enabled, qasr_encode keeps copies of intermediate activations for qasr_debug_read. */

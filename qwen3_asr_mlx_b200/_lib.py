@@ -43,6 +43,14 @@ class QasrStats(Structure):
     _fields_ = [("kernel_launches", c_uint64), ("workspace_bytes", c_uint64), ("weight_bytes", c_uint64)]
 
 
+PROF_CATEGORIES = 13
+
+
+class QasrProfile(Structure):
+    _fields_ = [("ms", ctypes.c_double * PROF_CATEGORIES), ("flops", ctypes.c_double * PROF_CATEGORIES),
+                ("bytes", ctypes.c_double * PROF_CATEGORIES), ("launches", c_uint64 * PROF_CATEGORIES)]
+
+
 class QasrError(RuntimeError):
     """A libqasr call failed with a non-argument error (CUDA, state, memory, unsupported)."""
 
@@ -68,6 +76,9 @@ _SIGNATURES = {
     "qasr_hann_window": (c_int, [POINTER(c_float)]),
     "qasr_positional_embedding": (c_int, [c_void_p, c_int32, POINTER(c_float)]),
     "qasr_get_stats": (c_int, [c_void_p, POINTER(QasrStats)]),
+    "qasr_set_profile": (c_int, [c_void_p, c_int]),
+    "qasr_get_profile": (c_int, [c_void_p, POINTER(QasrProfile)]),
+    "qasr_profile_name": (c_char_p, [c_int]),
     "qasr_set_debug": (c_int, [c_void_p, c_int]),
     "qasr_debug_read": (c_int, [c_void_p, c_char_p, POINTER(c_float), c_size_t]),
     "qasr_test_gemm": (c_int, [c_int, POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),

@@ -95,6 +95,12 @@ struct qasr_handle {
   DevBuf dbg_stem, dbg_layer0, dbg_hidden;
   long long dbg_tokens = 0;
   CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1;
+  // per-category CUDA-event profiling (qasr_set_profile)
+  bool profile = false;
+  struct ProfRec { int cat; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  qasr_profile prof_acc{};
   // pinned staging for tables
   void* pin = nullptr;
   size_t pin_bytes = 0;
@@ -115,6 +121,29 @@ int fail(qasr_handle* h, int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                         \
       return fail(h, QASR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
   } while (0)
+
+// Brackets one kernel launch with events on the launch stream when profiling is enabled.
+struct ProfScope {
+  qasr_handle* h;
+  cudaStream_t st;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(qasr_handle* h_, int cat, cudaStream_t st_, double flops, double bytes) : h(h_), st(st_) {
+    h->stats.kernel_launches++;
+    if (!h->profile) return;
+    cudaEvent_t e0 = nullptr;
+    for (cudaEvent_t* e : {&e0, &e1}) {
+      if (!h->prof_pool.empty()) { *e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+      else if (cudaEventCreate(e) != cudaSuccess) { *e = nullptr; }
+    }
+    if (!e0 || !e1) { e1 = nullptr; return; }
+    h->prof_acc.flops[cat] += flops;
+    h->prof_acc.bytes[cat] += bytes;
+    h->prof_acc.launches[cat] += 1;
+    cudaEventRecord(e0, st);
+    h->prof_recs.push_back({cat, e0, e1});
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
+};
 
 int dev_alloc(qasr_handle* h, DevBuf& b, size_t bytes, bool zero) {
   if (bytes <= b.bytes) return QASR_OK;
@@ -330,6 +359,7 @@ void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y,
   layernorm_bf16_kernel<VPL><<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, y, rows, 1e-5f);
 }
 int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
+  ProfScope ps(h, QASR_PROF_LAYERNORM, st, 0.0, 6.0 * rows * h->cfg.d_model);
   switch (h->cfg.d_model / 128) {
     case 1: launch_ln<1>(x, g, b, y, rows, st); break;
     case 2: launch_ln<2>(x, g, b, y, rows, st); break;
@@ -341,17 +371,16 @@ int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __
     case 8: launch_ln<8>(x, g, b, y, rows, st); break;
     default: return fail(h, QASR_ERR_UNSUPPORTED, "d_model");
   }
-  h->stats.kernel_launches++;
   QCUDA(h, cudaGetLastError());
   return QASR_OK;
 }
 
 template <int EPI>
-int dense(qasr_handle* h, const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, void* out, long long ldo,
-          const float* bias, cudaStream_t st) {
+int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, void* out,
+          long long ldo, const float* bias, cudaStream_t st) {
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
+  ProfScope ps(h, cat, st, 2.0 * M * N * K, 0.0);
   QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI>(ta, tw, p, st)));
-  h->stats.kernel_launches++;
   return QASR_OK;
 }
 
@@ -393,16 +422,21 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
   QCUDA(h, cudaMemsetAsync(h->d_uttmax.p, 0, static_cast<size_t>(B) * 4, st));
 
   MelTables tab{h->d_window, h->d_twiddle, h->d_fb_start, h->d_fb_count, h->d_fb_weight};
-  mel_logmel_kernel<<<boffs[B], kMelThreads, sizeof(MelSmem), st>>>(
-      audio_dev, static_cast<const long long*>(h->d_soffs.p), static_cast<const long long*>(h->d_foffs.p),
-      static_cast<const int*>(h->d_boffs.p), B, tab, mel_dev, static_cast<unsigned*>(h->d_uttmax.p));
+  {  // algorithmic bytes: audio read once + log-mel written once (115 200 B per audio-second)
+    ProfScope ps(h, QASR_PROF_MEL_LOGMEL, st, 0.0, 4.0 * soffs[B] + 4.0 * kMelBins * foffs[B]);
+    mel_logmel_kernel<<<boffs[B], kMelThreads, sizeof(MelSmem), st>>>(
+        audio_dev, static_cast<const long long*>(h->d_soffs.p), static_cast<const long long*>(h->d_foffs.p),
+        static_cast<const int*>(h->d_boffs.p), B, tab, mel_dev, static_cast<unsigned*>(h->d_uttmax.p));
+  }
   QCUDA(h, cudaGetLastError());
   const long long total_vec4 = foffs[B] * (kMelBins / 4);
   const long long nblk = (total_vec4 + kMelNormVecPerCta - 1) / kMelNormVecPerCta;
-  mel_normalize_kernel<<<static_cast<unsigned>(nblk), kMelNormThreads, 0, st>>>(
-      mel_dev, static_cast<const long long*>(h->d_foffs.p), B, static_cast<const unsigned*>(h->d_uttmax.p), total_vec4);
+  {
+    ProfScope ps(h, QASR_PROF_MEL_NORM, st, 0.0, 8.0 * kMelBins * foffs[B]);
+    mel_normalize_kernel<<<static_cast<unsigned>(nblk), kMelNormThreads, 0, st>>>(
+        mel_dev, static_cast<const long long*>(h->d_foffs.p), B, static_cast<const unsigned*>(h->d_uttmax.p), total_vec4);
+  }
   QCUDA(h, cudaGetLastError());
-  h->stats.kernel_launches += 2;
   if (frame_offsets_out) *frame_offsets_out = foffs;
   return QASR_OK;
 }
@@ -470,11 +504,13 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   const long long ps1 = G * 33 * 26 * kStemC, ps2 = G * 17 * 14 * kStemC;
   for (long long c0 = 0; c0 < nchunks; c0 += G) {
     const int g = static_cast<int>(nchunks - c0 < G ? nchunks - c0 : G);
-    conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
-        mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
-        static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+    {
+      ProfScope ps(h, QASR_PROF_CONV1, st, 2.0 * 64 * 50 * kStemC * 9 * g, (4.0 * 128 * 100 + 2.0 * 64 * 50 * kStemC) * g);
+      conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
+          mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
+          static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+    }
     QCUDA(h, cudaGetLastError());
-    h->stats.kernel_launches++;
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
       GemmParams p{};
       p.M = g * 33 * 25; p.N = kStemC; p.K = 9 * kStemC;
@@ -484,8 +520,8 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
       p.out = h->planes2.p; p.bias = h->conv2_b;
       p.out_Hp = 17; p.out_Wp = 14; p.out_plane_stride = ps2; p.out_C = kStemC;
+      ProfScope ps(h, QASR_PROF_CONV2, st, 2.0 * 32 * 25 * kStemC * 9 * kStemC * g, 0.0);
       QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES>(h->tm_planes1, h->tm_conv2_w, p, st)));
-      h->stats.kernel_launches++;
     }
     {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
       GemmParams p{};
@@ -495,15 +531,15 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.num_m_tiles = (g * 17 + 8) / 9;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
       p.out = h->flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
+      ProfScope ps(h, QASR_PROF_CONV3, st, 2.0 * 16 * 13 * kStemC * 9 * kStemC * g, 0.0);
       QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT>(h->tm_planes2, h->tm_conv3_w, p, st)));
-      h->stats.kernel_launches++;
     }
     {  // conv_out + positional embedding + strip padding + pack (encoder.py:277-293)
       GemmParams p = dense_params(g * kTokensPerChunk, D, 16 * kStemC, x, D, nullptr);
       p.row_map = static_cast<const int*>(h->d_rowmap.p) + c0 * kTokensPerChunk;
       p.pe = h->pe; p.pe_period = kTokensPerChunk;
+      ProfScope ps(h, QASR_PROF_CONV_OUT, st, 2.0 * g * kTokensPerChunk * D * 16 * kStemC, 0.0);
       QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK>(h->tm_flat3, h->tm_convout_w, p, st)));
-      h->stats.kernel_launches++;
     }
   }
   if (h->debug) {
@@ -517,18 +553,22 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   // ---- transformer layers (encoder.py:106-122)
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   const int ni = static_cast<int>(n);
+  double attn_flops = 0.0;  // 4 * w^2 * D per window of w tokens (QK^T and PV)
+  for (const WindowDesc& w : windows) attn_flops += 4.0 * w.len * w.len * D;
   for (size_t li = 0; li < h->layers.size(); ++li) {
     LayerWeights& L = h->layers[li];
     if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_STORE_BF16>(h, h->tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
-    window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
-        qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, h->tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
+    {
+      ProfScope ps(h, QASR_PROF_ATTENTION, st, attn_flops, 8.0 * n * D);
+      window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
+          qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+    }
     QCUDA(h, cudaGetLastError());
-    h->stats.kernel_launches++;
-    if ((rc = dense<EPI_RESID_F32>(h, h->tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, h->tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
     if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_GELU_BF16>(h, h->tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
-    if ((rc = dense<EPI_RESID_F32>(h, h->tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
+    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, h->tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, h->tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
     if (h->debug && li == 0)
       QCUDA(h, cudaMemcpyAsync(h->dbg_layer0.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -536,11 +576,11 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
 
   // ---- projector (encoder.py:319-321)
   if ((rc = layernorm(h, x, h->lnp_g, h->lnp_b, xn, ni, st))) return rc;
-  if ((rc = dense<EPI_GELU_BF16>(h, h->tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
+  if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_PROJ, h->tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
   if (out_dtype == QASR_F32) {
-    if ((rc = dense<EPI_STORE_F32>(h, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+    if ((rc = dense<EPI_STORE_F32>(h, QASR_PROF_GEMM_PROJ, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
   } else {
-    if ((rc = dense<EPI_STORE_BF16>(h, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_PROJ, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
   }
   return QASR_OK;
 }
@@ -602,6 +642,8 @@ void qasr_destroy(qasr_handle* h) {
                     &h->io_in, &h->io_out, &h->d_chunks, &h->d_rowmap, &h->d_windows, &h->d_soffs, &h->d_foffs,
                     &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden};
   for (DevBuf* b : bufs) dev_free(h, *b);
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_event) cudaEventDestroy(h->pin_event);
   delete h;
@@ -848,6 +890,41 @@ int qasr_get_stats(const qasr_handle* h, qasr_stats* out) {
   if (!h || !out) return fail(nullptr, QASR_ERR_INVALID, "null argument");
   *out = h->stats;
   return QASR_OK;
+}
+
+int qasr_set_profile(qasr_handle* h, int enabled) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  QCUDA(h, cudaDeviceSynchronize());
+  for (auto& r : h->prof_recs) { h->prof_pool.push_back(r.e0); h->prof_pool.push_back(r.e1); }
+  h->prof_recs.clear();
+  h->prof_acc = qasr_profile{};
+  h->profile = enabled != 0;
+  return QASR_OK;
+}
+
+int qasr_get_profile(qasr_handle* h, qasr_profile* out) {
+  if (!h || !out) return fail(h, QASR_ERR_INVALID, "qasr_get_profile: null argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  QCUDA(h, cudaDeviceSynchronize());
+  for (auto& r : h->prof_recs) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) h->prof_acc.ms[r.cat] += ms;
+    h->prof_pool.push_back(r.e0);
+    h->prof_pool.push_back(r.e1);
+  }
+  h->prof_recs.clear();
+  *out = h->prof_acc;
+  return QASR_OK;
+}
+
+const char* qasr_profile_name(int category) {
+  static const char* names[QASR_PROF_CATEGORIES] = {"mel_logmel", "mel_normalize", "conv1", "conv2_igemm", "conv3_igemm",
+                                                    "conv_out_gemm", "layernorm", "gemm_qkv", "window_attention",
+                                                    "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_projector"};
+  return (category >= 0 && category < QASR_PROF_CATEGORIES) ? names[category] : "";
 }
 
 int qasr_set_debug(qasr_handle* h, int enabled) {

@@ -209,6 +209,20 @@ class AudioEncoder:
     def stats(self) -> Dict[str, int]:
         return self._handle.stats()
 
+    def set_profile(self, enabled: bool) -> None:
+        """Bracket every kernel launch with CUDA events on the launch stream (resets the totals)."""
+        self._handle.check(self._handle.lib.qasr_set_profile(self._handle.ptr, int(enabled)))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-category totals since ``set_profile``: device ms, algorithmic flops/bytes, launches."""
+        prof = _lib.QasrProfile()
+        self._handle.check(self._handle.lib.qasr_get_profile(self._handle.ptr, ctypes.byref(prof)))
+        out = {}
+        for i in range(_lib.PROF_CATEGORIES):
+            name = self._handle.lib.qasr_profile_name(i).decode()
+            out[name] = {"ms": prof.ms[i], "flops": prof.flops[i], "bytes": prof.bytes[i], "launches": int(prof.launches[i])}
+        return out
+
     def reserve(self, total_frames: int, batch: int) -> None:
         self._handle.check(self._handle.lib.qasr_reserve(self._handle.ptr, int(total_frames), int(batch)))
 

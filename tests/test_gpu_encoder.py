@@ -1,0 +1,197 @@
+"""GPU parity of the audio encoder (through the C ABI) against the oracle.
+Tolerance: embedding relative (Frobenius) error <= 2e-2, bf16 kernels vs the fp32 oracle
+(BASELINE.json north_star).  Shape contract mirrored from reference tests/test_encoder.py."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from helpers import EMB_TOL, bf16_bits, bf16_round, rel_err, synth
+from oracle import encoder_torch, mel_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _small():
+    from qwen3_asr_mlx_b200 import AudioEncoderConfig
+
+    return AudioEncoderConfig(d_model=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_dim=512, output_dim=256)
+
+
+@pytest.fixture(scope="module")
+def small():
+    from qwen3_asr_mlx_b200 import AudioEncoder, weights
+
+    cfg = _small()
+    params = weights.random_init(cfg, seed=7, exercise_all=True)
+    enc = AudioEncoder(cfg)
+    enc.load_weights(params)
+    yield cfg, params, enc
+    enc.close()
+
+
+@pytest.fixture(scope="module")
+def full():
+    from qwen3_asr_mlx_b200 import AudioEncoder, AudioEncoderConfig, weights
+
+    cfg = AudioEncoderConfig()
+    params = weights.random_init(cfg, seed=1234)
+    enc = AudioEncoder(cfg)
+    enc.load_weights(params)
+    yield cfg, params, enc
+    enc.close()
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (1, 256, 64), (300, 1024, 1024), (130, 2048, 4096), (1000, 3072, 1024)])
+def test_tcgen05_gemm_kernel(shape):
+    from qwen3_asr_mlx_b200 import _lib
+
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    a = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = bf16_round((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32))
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = np.zeros((M, N), dtype=np.float32)
+    lib = _lib.load()
+    u16, f32 = ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_float)
+    ab, wb = bf16_bits(a), bf16_bits(w)
+    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 0, out.ctypes.data_as(f32)))
+    ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
+    assert np.abs(out - ref).max() <= 1e-4  # fp32 accumulation of exact bf16 products
+
+
+@pytest.mark.parametrize("n_samples", [160, 16000, 16000 * 4 + 7000, 16000 * 9 + 4321, 16000 * 20 + 333])
+def test_small_config_parity_with_intermediates(small, n_samples):
+    cfg, params, enc = small
+    mel = mel_np.log_mel_spectrogram_fast(synth(np.random.default_rng(n_samples), n_samples))
+    ref, inter = encoder_torch.encoder_forward(params, cfg, mel, return_intermediates=True)
+    enc.set_debug(True)
+    out = np.array(enc(mel))
+    assert out.shape == (1,) + ref.shape
+    for k in ("stem", "layer0", "hidden"):
+        assert rel_err(enc.debug_read(k, ref.shape[0]), inter[k]) <= EMB_TOL, k
+    enc.set_debug(False)
+    assert rel_err(out[0], ref) <= EMB_TOL
+
+
+def test_golden_anchor(small, golden_dir):
+    cfg, params, enc = small
+    g = np.load(os.path.join(golden_dir, "encoder_small.npz"))
+    from qwen3_asr_mlx_b200 import log_mel_spectrogram
+
+    out = np.array(enc(log_mel_spectrogram(g["audio"])))[0]  # CUDA mel feeding the CUDA encoder
+    assert out.shape == g["emb"].shape
+    assert rel_err(out, g["emb"]) <= EMB_TOL
+
+
+@pytest.mark.parametrize("T,tokens", [(100, 13), (300, 39), (250, 33), (50, 7), (1, 1)])
+def test_reference_shape_contract(small, T, tokens):
+    # reference tests/test_encoder.py:64-97
+    cfg, params, enc = small
+    mel = np.random.default_rng(T).standard_normal((128, T)).astype(np.float32)
+    out = enc(mel)
+    assert out.shape == (1, tokens, cfg.output_dim)
+    assert np.isfinite(np.array(out)).all()
+    batched = enc(mel[None])  # (1, 128, T) accepted
+    assert np.array_equal(np.array(batched), np.array(out))
+
+
+def test_bad_input_shapes(small):
+    cfg, params, enc = small
+    with pytest.raises(ValueError):
+        enc(np.zeros((64, 100), dtype=np.float32))
+    with pytest.raises(ValueError):
+        enc.encode_batch([])
+
+
+def test_varlen_batch_equals_loop_of_singles(small):
+    cfg, params, enc = small
+    rng = np.random.default_rng(5)
+    mels = [mel_np.log_mel_spectrogram_fast(synth(rng, int(n))) for n in (16000, 200000, 160 * 57, 16000 * 9, 160, 480000)]
+    emb, toffs = enc.encode_batch(mels)
+    e = np.array(emb)
+    assert list(np.diff(toffs)) == [enc.num_tokens(m.shape[1]) for m in mels]
+    for u, m in enumerate(mels):
+        single = np.array(enc(m))[0]
+        assert np.array_equal(e[int(toffs[u]): int(toffs[u + 1])], single)  # batching must not change results
+        assert rel_err(single, encoder_torch.encoder_forward(params, cfg, m)) <= EMB_TOL
+
+
+def test_windows_are_independent(small):
+    """Block-diagonal attention without a mask tensor: tokens of the first 8-s window do not depend on later audio."""
+    cfg, params, enc = small
+    mel = np.random.default_rng(3).standard_normal((128, 1000)).astype(np.float32)
+    mel2 = mel.copy()
+    mel2[:, 800:] += 1.0
+    a, b = np.array(enc(mel))[0], np.array(enc(mel2))[0]
+    assert a.shape == (130, cfg.output_dim)
+    assert np.array_equal(a[:104], b[:104]) and not np.allclose(a[104:], b[104:])
+
+
+def test_stem_grouping_is_transparent(small, monkeypatch):
+    """The conv stem runs in bounded groups of chunks; a tiny group size must give identical results."""
+    from qwen3_asr_mlx_b200 import AudioEncoder
+
+    cfg, params, enc = small
+    mel = mel_np.log_mel_spectrogram_fast(synth(np.random.default_rng(9), 16000 * 12 + 5000))
+    ref = np.array(enc(mel))
+    monkeypatch.setenv("QASR_STEM_GROUP", "3")
+    enc2 = AudioEncoder(cfg)
+    enc2.load_weights(params)
+    assert np.array_equal(np.array(enc2(mel)), ref)
+    enc2.close()
+
+
+def test_full_arch_config1_parity(full):
+    """BASELINE config 1: one 10 s utterance, Qwen3-ASR-1.7B encoder architecture, random init (seed 1234)."""
+    cfg, params, enc = full
+    x = synth(np.random.default_rng(0), 160000)
+    mel = mel_np.log_mel_spectrogram_fast(x)
+    ref = encoder_torch.encoder_forward(params, cfg, mel)
+    out = np.array(enc(mel))
+    assert out.shape == (1, 130, 2048)
+    assert rel_err(out[0], ref) <= EMB_TOL
+    emb, toffs = enc.encode_audio_batch([x])  # mel + encoder back to back on the device
+    assert list(toffs) == [0, 130] and rel_err(np.array(emb), ref) <= EMB_TOL
+    bf = np.array(enc.encode_audio_batch([x], out_dtype="bfloat16")[0])
+    assert rel_err(bf, ref) <= EMB_TOL
+    # per-utterance worst case over a few lengths (mixed-length, config 3 style)
+    rng = np.random.default_rng(3)
+    xs = [synth(rng, int(n)) for n in (16000, 77777, 250000)]
+    emb, toffs = enc.encode_audio_batch(xs)
+    e = np.array(emb)
+    for u, xu in enumerate(xs):
+        r = encoder_torch.encoder_forward(params, cfg, mel_np.log_mel_spectrogram_fast(xu))
+        assert rel_err(e[int(toffs[u]): int(toffs[u + 1])], r) <= EMB_TOL
+
+
+def test_full_arch_host_entry_point(full):
+    cfg, params, enc = full
+    rng = np.random.default_rng(8)
+    xs = [synth(rng, 48000), synth(rng, 20000)]
+    packed = np.concatenate(xs)
+    soffs = np.array([0, 48000, 68000], dtype=np.int64)
+    n_tok = enc.num_tokens(300) + enc.num_tokens(125)
+    out = np.empty((n_tok, 2048), dtype=np.float32)
+    toffs = enc.encode_audio_host(packed, soffs, out)
+    dev, toffs2 = enc.encode_audio_batch(xs)
+    assert list(toffs) == list(toffs2) and np.array_equal(out, np.array(dev))
+
+
+def test_full_arch_config2_size_properties(full):
+    """BASELINE config 2 size (64 x 30 s on one B200): shape, finiteness, batch == single, spot parity."""
+    cfg, params, enc = full
+    rng = np.random.default_rng(1)
+    base = [synth(rng, 480000) for _ in range(4)]
+    xs = [base[i % 4] for i in range(64)]
+    emb, toffs = enc.encode_audio_batch(xs)
+    e = np.array(emb)
+    assert e.shape == (24960, 2048) and np.isfinite(e).all()
+    assert list(np.diff(toffs)) == [390] * 64
+    for u in range(4, 64):  # identical audio -> identical embeddings wherever it sits in the batch
+        assert np.array_equal(e[390 * u: 390 * (u + 1)], e[390 * (u % 4): 390 * (u % 4 + 1)])
+    single = np.array(enc.encode_audio_batch([xs[2]])[0])
+    assert np.array_equal(single, e[780:1170])
+    ref = encoder_torch.encoder_forward(params, cfg, mel_np.log_mel_spectrogram_fast(xs[2]))
+    assert rel_err(single, ref) <= EMB_TOL
