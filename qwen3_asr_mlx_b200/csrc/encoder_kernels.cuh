@@ -165,7 +165,114 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kAttnThreads)
+// ------------------------------------------------------------------------------ conv1 on tensor cores
+// Same contract as conv1_gelu_kernel, but the 9-tap contraction runs on mma.sync.m16n8k16
+// (K = 9 taps zero-padded to 16).  The fp32 mel patch is split into bf16 hi + lo parts and fed
+// through two MMAs, so the input keeps ~16 mantissa bits; weights are bf16 like every other
+// layer.  What remains on the CUDA cores is bias + GELU + pack + store.
+// Warp w owns channels [96w, 96w+96) = 3 groups of 32 = 12 n-tiles; within a group, tile j
+// column n maps to channel 8*(n/2) + 2*j + (n&1), so each thread ends up holding 8 consecutive
+// channels of a pixel (one 16-byte store).
+constexpr int kConv1TcWarps = 5;
+constexpr int kConv1TcThreads = kConv1TcWarps * 32;
+
+template <int C>
+__global__ void __launch_bounds__(kConv1TcThreads, 3)
+conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ chunks, int chunk0,
+                     const __nv_bfloat16* __restrict__ w /*[C][9] bf16*/, const float* __restrict__ bias /*[C]*/,
+                     __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+  static_assert(C == 96 * kConv1TcWarps, "warp/channel mapping assumes C == 480");
+  constexpr int IW = 104;
+  __shared__ float in[2 * kConv1RowsPerCta + 1][IW];
+
+  const int b = blockIdx.x / (64 / kConv1RowsPerCta);
+  const int part = blockIdx.x % (64 / kConv1RowsPerCta);
+  const int oh0 = part * kConv1RowsPerCta;
+  const ChunkDesc cd = chunks[chunk0 + b];
+  const float* __restrict__ src = mel + cd.mel_base;
+  const int valid_w = min(100, cd.T - cd.frame0);
+  for (int i = threadIdx.x; i < (2 * kConv1RowsPerCta + 1) * 102; i += kConv1TcThreads) {
+    const int r = i / 102, c = i - r * 102;
+    const int h = 2 * oh0 - 1 + r, wv = c - 1;
+    float v = 0.0f;
+    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+    in[r][c] = v;
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int cwarp = warp * 96;
+  // B fragments (weights) and biases stay in registers for the whole CTA
+  uint32_t bw0[12], bw1[12];
+  float bs[3][8];
+#pragma unroll
+  for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = cwarp + grp * 32 + 8 * (g >> 1) + 2 * j + (g & 1);  // column n = g of tile j
+      const __nv_bfloat16* wr = w + ch * 9;
+      const uint32_t lo = *reinterpret_cast<const unsigned short*>(wr + 2 * t);
+      const uint32_t hi = *reinterpret_cast<const unsigned short*>(wr + 2 * t + 1);
+      bw0[grp * 4 + j] = lo | (hi << 16);                                                   // k = 2t, 2t+1
+      bw1[grp * 4 + j] = (t == 0) ? static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(wr + 8)) : 0u;  // k = 8, (9 = 0)
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bs[grp][i] = __ldg(bias + cwarp + grp * 32 + 8 * t + i);
+  }
+  __syncthreads();
+
+  const int kh0 = (2 * t) / 3, kw0 = (2 * t) % 3, kh1 = (2 * t + 1) / 3, kw1 = (2 * t + 1) % 3;
+  for (int mb = 0; mb < (kConv1RowsPerCta * 50) / 16; ++mb) {
+    const int p_lo = mb * 16 + g, p_hi = p_lo + 8;
+    const int oh_lo = p_lo / 50, ow_lo = p_lo - oh_lo * 50;
+    const int oh_hi = p_hi / 50, ow_hi = p_hi - oh_hi * 50;
+    const float v0 = in[2 * oh_lo + kh0][2 * ow_lo + kw0], v1 = in[2 * oh_lo + kh1][2 * ow_lo + kw1];
+    const float v2 = in[2 * oh_hi + kh0][2 * ow_hi + kw0], v3 = in[2 * oh_hi + kh1][2 * ow_hi + kw1];
+    const float v4 = (t == 0) ? in[2 * oh_lo + 2][2 * ow_lo + 2] : 0.0f;
+    const float v5 = (t == 0) ? in[2 * oh_hi + 2][2 * ow_hi + 2] : 0.0f;
+    uint32_t ahi[4], alo[4];
+    {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2),
+                          h3 = __float2bfloat16_rn(v3), h4 = __float2bfloat16_rn(v4), h5 = __float2bfloat16_rn(v5);
+      ahi[0] = ptx::pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+      ahi[1] = ptx::pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
+      ahi[2] = ptx::pack_bf16x2(__bfloat162float(h4), 0.0f);
+      ahi[3] = ptx::pack_bf16x2(__bfloat162float(h5), 0.0f);
+      alo[0] = ptx::pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+      alo[1] = ptx::pack_bf16x2(v2 - __bfloat162float(h2), v3 - __bfloat162float(h3));
+      alo[2] = ptx::pack_bf16x2(v4 - __bfloat162float(h4), 0.0f);
+      alo[3] = ptx::pack_bf16x2(v5 - __bfloat162float(h5), 0.0f);
+    }
+    const int h_lo = oh0 + oh_lo, h_hi = oh0 + oh_hi;
+    __nv_bfloat16* d_lo = planes + (2 * (h_lo & 1) + (ow_lo & 1)) * plane_stride +
+                          ((static_cast<long long>(b) * 33 + (h_lo >> 1) + 1) * 26 + (ow_lo >> 1) + 1) * C + cwarp + 8 * t;
+    __nv_bfloat16* d_hi = planes + (2 * (h_hi & 1) + (ow_hi & 1)) * plane_stride +
+                          ((static_cast<long long>(b) * 33 + (h_hi >> 1) + 1) * 26 + (ow_hi >> 1) + 1) * C + cwarp + 8 * t;
+#pragma unroll
+    for (int grp = 0; grp < 3; ++grp) {
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+        mma_bf16_16816(acc[j], ahi, bw0[grp * 4 + j], bw1[grp * 4 + j]);
+        mma_bf16_16816(acc[j], alo, bw0[grp * 4 + j], bw1[grp * 4 + j]);
+      }
+      uint4 q_lo, q_hi;
+      q_lo.x = ptx::pack_bf16x2(gelu_fast(acc[0][0] + bs[grp][0]), gelu_fast(acc[0][1] + bs[grp][1]));
+      q_lo.y = ptx::pack_bf16x2(gelu_fast(acc[1][0] + bs[grp][2]), gelu_fast(acc[1][1] + bs[grp][3]));
+      q_lo.z = ptx::pack_bf16x2(gelu_fast(acc[2][0] + bs[grp][4]), gelu_fast(acc[2][1] + bs[grp][5]));
+      q_lo.w = ptx::pack_bf16x2(gelu_fast(acc[3][0] + bs[grp][6]), gelu_fast(acc[3][1] + bs[grp][7]));
+      q_hi.x = ptx::pack_bf16x2(gelu_fast(acc[0][2] + bs[grp][0]), gelu_fast(acc[0][3] + bs[grp][1]));
+      q_hi.y = ptx::pack_bf16x2(gelu_fast(acc[1][2] + bs[grp][2]), gelu_fast(acc[1][3] + bs[grp][3]));
+      q_hi.z = ptx::pack_bf16x2(gelu_fast(acc[2][2] + bs[grp][4]), gelu_fast(acc[2][3] + bs[grp][5]));
+      q_hi.w = ptx::pack_bf16x2(gelu_fast(acc[3][2] + bs[grp][6]), gelu_fast(acc[3][3] + bs[grp][7]));
+      *reinterpret_cast<uint4*>(d_lo + grp * 32) = q_lo;
+      *reinterpret_cast<uint4*>(d_hi + grp * 32) = q_hi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 3)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const WindowDesc* __restrict__ windows,
                         __nv_bfloat16* __restrict__ out, int D, float scale_log2e) {
   __shared__ __align__(16) __nv_bfloat16 sK[kAttnMaxWin * kAttnPitch];

@@ -129,6 +129,24 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[W], const G
   }
 }
 
+// Residual update with the old values already in registers: out[m, n..n+W) = res + acc + bias.
+template <int W>
+__device__ __forceinline__ void epilogue_resid(const uint32_t (&acc)[W], const float4 (&res)[W / 4], const GemmParams& p,
+                                               int n, void* row_ptr) {
+  float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i) {
+    float4 b = p.bias != nullptr ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t = res[i];
+    t.x += __uint_as_float(acc[4 * i + 0]) + b.x;
+    t.y += __uint_as_float(acc[4 * i + 1]) + b.y;
+    t.z += __uint_as_float(acc[4 * i + 2]) + b.z;
+    t.w += __uint_as_float(acc[4 * i + 3]) + b.w;
+    dst[i] = t;
+  }
+}
+
 template <int BLOCK_N, int kStages, int kAMode, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -289,17 +307,53 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
 
+      // Residual prefetch: the fp32 rows this thread will update do not depend on the accumulator,
+      // so their first chunk is requested before waiting for the MMA to finish.
+      [[maybe_unused]] float4 res_next[kChunk / 4];
+      if constexpr (kEpi == EPI_RESID_F32) {
+        if (row_ptr != nullptr && n0 + half * kChunk < p.N) {
+          const float4* src = reinterpret_cast<const float4*>(static_cast<float*>(row_ptr) + n0 + half * kChunk);
+#pragma unroll
+          for (int i = 0; i < kChunk / 4; ++i) res_next[i] = src[i];
+        }
+      }
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccumStride;
+      // Two-deep software pipeline over the column chunks: the TMEM load (and residual load) of
+      // chunk j+2 is in flight while chunk j is converted and stored.
+      uint32_t acc_cur[kChunk], acc_next[kChunk];
+      if (half < kNumChunks) {
+        if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + half * kChunk, acc_next);
+        else ptx::tmem_ld_32x16(taddr + half * kChunk, acc_next);
+      }
 #pragma unroll 1
       for (int j = half; j < kNumChunks; j += 2) {
-        uint32_t acc[kChunk];
-        if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + j * kChunk, acc);
-        else ptx::tmem_ld_32x16(taddr + j * kChunk, acc);
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) acc_cur[i] = acc_next[i];
+        [[maybe_unused]] float4 res_cur[kChunk / 4];
+        if constexpr (kEpi == EPI_RESID_F32) {
+#pragma unroll
+          for (int i = 0; i < kChunk / 4; ++i) res_cur[i] = res_next[i];
+        }
+        const int jn = j + 2;
+        if (jn < kNumChunks) {
+          if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + jn * kChunk, acc_next);
+          else ptx::tmem_ld_32x16(taddr + jn * kChunk, acc_next);
+          if constexpr (kEpi == EPI_RESID_F32) {
+            if (row_ptr != nullptr && n0 + jn * kChunk < p.N) {
+              const float4* src = reinterpret_cast<const float4*>(static_cast<float*>(row_ptr) + n0 + jn * kChunk);
+#pragma unroll
+              for (int i = 0; i < kChunk / 4; ++i) res_next[i] = src[i];
+            }
+          }
+        }
         const int n = n0 + j * kChunk;
-        if (row_ptr != nullptr && n < p.N) epilogue_chunk<kEpi, kChunk>(acc, p, n, row_ptr, pe_row);
+        if (row_ptr != nullptr && n < p.N) {
+          if constexpr (kEpi == EPI_RESID_F32) epilogue_resid<kChunk>(acc_cur, res_cur, p, n, row_ptr);
+          else epilogue_chunk<kEpi, kChunk>(acc_cur, p, n, row_ptr, pe_row);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -67,6 +67,7 @@ struct qasr_handle {
   std::string err;
   bool finalized = false;
   bool debug = false;
+  bool conv1_fp32 = false;  // QASR_CONV1_FP32=1 selects the CUDA-core fp32-weight conv1 (A/B testing)
   qasr_stats stats{};
 
   std::map<std::string, std::vector<float>> staged;  // host copies until finalize
@@ -80,6 +81,7 @@ struct qasr_handle {
   float* d_fb_weight = nullptr;
 
   // encoder weights
+  __nv_bfloat16* conv1_w_bf16 = nullptr;
   float *conv1_w = nullptr, *conv1_b = nullptr, *conv2_b = nullptr, *conv3_b = nullptr;
   __nv_bfloat16 *conv2_w = nullptr, *conv3_w = nullptr, *convout_w = nullptr, *proj1_w = nullptr, *proj2_w = nullptr;
   float *proj1_b = nullptr, *proj2_b = nullptr, *lnp_g = nullptr, *lnp_b = nullptr, *pe = nullptr;
@@ -506,9 +508,14 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
     const int g = static_cast<int>(nchunks - c0 < G ? nchunks - c0 : G);
     {
       ProfScope ps(h, QASR_PROF_CONV1, st, 2.0 * 64 * 50 * kStemC * 9 * g, (4.0 * 128 * 100 + 2.0 * 64 * 50 * kStemC) * g);
-      conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
-          mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
-          static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+      if (h->conv1_fp32)
+        conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
+            mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
+            static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+      else
+        conv1_gelu_tc_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1TcThreads, 0, st>>>(
+            mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
+            static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
     }
     QCUDA(h, cudaGetLastError());
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
@@ -622,6 +629,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   int rc = validate_config(h, *cfg);
   if (rc) { g_last_error = h->err; delete h; return rc; }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaSetDevice failed"); }
+  if (const char* c1 = getenv("QASR_CONV1_FP32")) h->conv1_fp32 = atoi(c1) != 0;
   if (const char* sg = getenv("QASR_STEM_GROUP")) {
     const int v = atoi(sg);
     if (v > 0) h->stem_group = v;
@@ -680,6 +688,7 @@ int qasr_finalize_weights(qasr_handle* h) {
   if (!take(h, name, count, vec, miss)) return fail(h, QASR_ERR_STATE, "parameter " + miss)
   TAKE("conv2d1.weight", C * 9, w); TAKE("conv2d1.bias", C, b);
   if ((rc = upload<float>(h, &h->conv1_w, w)) || (rc = upload<float>(h, &h->conv1_b, b))) return rc;
+  if ((rc = upload_bf16(h, &h->conv1_w_bf16, w))) return rc;
   TAKE("conv2d2.weight", C * 9 * C, w); TAKE("conv2d2.bias", C, b);
   if ((rc = upload_bf16(h, &h->conv2_w, w)) || (rc = upload<float>(h, &h->conv2_b, b))) return rc;
   TAKE("conv2d3.weight", C * 9 * C, w); TAKE("conv2d3.bias", C, b);
