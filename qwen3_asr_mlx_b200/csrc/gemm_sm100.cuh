@@ -4,7 +4,14 @@
 //   warp 1      MMA issuer        (one elected lane; tcgen05.mma kind::f16, fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator
 //   warp 3      idle
-//   warps 4-11  epilogue          (tcgen05.ld -> registers -> bias / GELU / residual / scatter -> global)
+//   warps 4-11  epilogue          (tcgen05.ld -> registers -> swizzled smem transpose -> bias / GELU /
+//                                  residual / scatter -> coalesced global accesses)
+//
+// Epilogue data path: tcgen05.ld hands each thread one accumulator ROW (32 lanes x 32 columns per
+// warp).  Storing rows straight from registers makes every warp-level access touch 32 different
+// cache lines; instead each warp transposes its 32 x 32 (or 32 x 16) block through a private,
+// XOR-swizzled shared-memory buffer so that a warp instruction covers whole 64-128 byte row
+// segments (4-16 lines per instruction instead of 32).
 //
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the
 // main loop of tile i+1.  The same kernel serves every dense contraction on the encoder
@@ -68,83 +75,21 @@ struct GemmSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kEpiStageBytes = 8 * 32 * 32 * 4;  // 8 epilogue warps x (32 rows x 128 B)
+  static constexpr int kEpiRowBytes = 8 * 32 * 4;         // per-warp destination row table
+  static constexpr int kTotal = kStages * kStageBytes + kEpiStageBytes + kEpiRowBytes + kBarrierBytes + 1024;
 };
 
-template <int kEpi, int W>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[W], const GemmParams& p, int n, void* row_ptr,
-                                               int pe_row) {
-  // row_ptr points at element (dest_row, 0) of the destination; n is the absolute column.
-  float v[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) v[i] = __uint_as_float(acc[i]);
-  if constexpr (kEpi == EPI_CONVOUT_PACK) {
-    const float4* pe4 = reinterpret_cast<const float4*>(p.pe + static_cast<long long>(pe_row) * p.N + n);
-#pragma unroll
-    for (int i = 0; i < W / 4; ++i) {
-      float4 t = __ldg(pe4 + i);
-      v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
-  } else {
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-      for (int i = 0; i < W / 4; ++i) {
-        float4 t = __ldg(b4 + i);
-        v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-      }
-    }
-  }
-  if constexpr (kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) v[i] = gelu_fast(v[i]);  // output is rounded to bf16 below
-  } else if constexpr (kEpi == EPI_GELU_F32) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
-  }
-  if constexpr (kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES ||
-                kEpi == EPI_CONV_FLAT) {
-    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(row_ptr) + n);
-#pragma unroll
-    for (int i = 0; i < W / 8; ++i) {
-      uint4 q;
-      q.x = ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      q.y = ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      q.z = ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      q.w = ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      dst[i] = q;
-    }
-  } else if constexpr (kEpi == EPI_RESID_F32) {
-    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
-#pragma unroll
-    for (int i = 0; i < W / 4; ++i) {
-      float4 t = dst[i];
-      t.x += v[4 * i + 0]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
-      dst[i] = t;
-    }
-  } else {  // EPI_STORE_F32, EPI_CONVOUT_PACK, EPI_GELU_F32
-    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
-#pragma unroll
-    for (int i = 0; i < W / 4; ++i) dst[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
+// 16-byte-unit XOR swizzle of a per-warp staging buffer with U units per row (U = 8, 4 or 2):
+// conflict-free for both the row-owner writes and the transposed reads.
+template <int U>
+__device__ __forceinline__ int stage_unit(int row, int unit) {
+  return row * U + (unit ^ ((row / (8 / U)) % U));
 }
 
-// Residual update with the old values already in registers: out[m, n..n+W) = res + acc + bias.
-template <int W>
-__device__ __forceinline__ void epilogue_resid(const uint32_t (&acc)[W], const float4 (&res)[W / 4], const GemmParams& p,
-                                               int n, void* row_ptr) {
-  float4* dst = reinterpret_cast<float4*>(static_cast<float*>(row_ptr) + n);
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-  for (int i = 0; i < W / 4; ++i) {
-    float4 b = p.bias != nullptr ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 t = res[i];
-    t.x += __uint_as_float(acc[4 * i + 0]) + b.x;
-    t.y += __uint_as_float(acc[4 * i + 1]) + b.y;
-    t.z += __uint_as_float(acc[4 * i + 2]) + b.z;
-    t.w += __uint_as_float(acc[4 * i + 3]) + b.w;
-    dst[i] = t;
-  }
+template <int kEpi>
+constexpr bool epi_is_bf16() {
+  return kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT;
 }
 
 template <int BLOCK_N, int kStages, int kAMode, int kEpi>
@@ -167,6 +112,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* epi_base = smem + kStages * L::kStageBytes + L::kBarrierBytes;  // 16-byte aligned
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,10 +204,16 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------------ epilogue
+    constexpr bool kBf16Out = epi_is_bf16<kEpi>();
+    constexpr int U = kBf16Out ? kChunk / 8 : kChunk / 4;  // 16-byte units per staged row
+    static_assert(kBf16Out || kChunk == 32, "fp32 epilogues assume 32-column chunks");
     const int ew = warp_idx - 4;
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     const int half = ew >> 2;          // interleaved column chunks
-    const int r = quarter * 32 + lane;  // tile row == TMEM lane
+    const int r = quarter * 32 + lane;  // tile row == TMEM lane owned by this thread
+    uint4* stg = reinterpret_cast<uint4*>(epi_base) + ew * (32 * 8);
+    int* rowdst = reinterpret_cast<int*>(epi_base + L::kEpiStageBytes) + ew * 32;
+    const long long row_stride = (kAMode == A_ROWS) ? p.ldo : static_cast<long long>(p.out_C);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -269,91 +221,131 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n_blk = tile % p.num_n_tiles;
       const int n0 = n_blk * BLOCK_N;
 
-      // Resolve this thread's destination row once per tile.
-      void* row_ptr = nullptr;
-      int pe_row = 0;
+      // Destination row (or pixel) index of this thread's accumulator row, -1 if it is not stored.
+      int dst = -1;
       if constexpr (kAMode == A_ROWS) {
         const int m = m_blk * kBlockM + r;
-        if (m < p.M) {
-          if constexpr (kEpi == EPI_CONVOUT_PACK) {
-            const int dst = __ldg(p.row_map + m);
-            pe_row = m % p.pe_period;
-            if (dst >= 0) row_ptr = static_cast<float*>(p.out) + static_cast<long long>(dst) * p.ldo;
-          } else if constexpr (kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16) {
-            row_ptr = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo;
-          } else {
-            row_ptr = static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo;
-          }
-        }
+        if (m < p.M) dst = (kEpi == EPI_CONVOUT_PACK) ? __ldg(p.row_map + m) : m;
       } else {
         // tile row r -> (padded output row, ow) -> (chunk, oh, ow)
         const int rr = r / p.conv_OW;
         const int ow = r - rr * p.conv_OW;
         if (rr < p.conv_rows_per_tile) {
-          const int g = m_blk * p.conv_rows_per_tile + rr;
-          const int b = g / p.conv_OHp;
-          const int oh = g - b * p.conv_OHp;
+          const int gg = m_blk * p.conv_rows_per_tile + rr;
+          const int b = gg / p.conv_OHp;
+          const int oh = gg - b * p.conv_OHp;
           if (b < p.conv_chunks && oh < p.conv_OH) {
             if constexpr (kEpi == EPI_CONV_PLANES) {
               const int plane = 2 * (oh & 1) + (ow & 1);
-              const long long pix =
-                  (static_cast<long long>(b) * p.out_Hp + (oh >> 1) + 1) * p.out_Wp + (ow >> 1) + 1;
-              row_ptr = static_cast<__nv_bfloat16*>(p.out) + plane * p.out_plane_stride + pix * p.out_C;
+              dst = static_cast<int>(plane * (p.out_plane_stride / p.out_C)) +
+                    ((b * p.out_Hp + (oh >> 1) + 1) * p.out_Wp + (ow >> 1) + 1);
             } else {  // EPI_CONV_FLAT
-              const long long pix = (static_cast<long long>(b) * p.conv_OW + ow) * p.conv_OH + oh;
-              row_ptr = static_cast<__nv_bfloat16*>(p.out) + pix * p.out_C;
+              dst = (b * p.conv_OW + ow) * p.conv_OH + oh;
             }
           }
         }
       }
+      __syncwarp();  // previous tile's readers are done with rowdst / stg
+      rowdst[lane] = dst;
 
-      // Residual prefetch: the fp32 rows this thread will update do not depend on the accumulator,
-      // so their first chunk is requested before waiting for the MMA to finish.
-      [[maybe_unused]] float4 res_next[kChunk / 4];
-      if constexpr (kEpi == EPI_RESID_F32) {
-        if (row_ptr != nullptr && n0 + half * kChunk < p.N) {
-          const float4* src = reinterpret_cast<const float4*>(static_cast<float*>(row_ptr) + n0 + half * kChunk);
-#pragma unroll
-          for (int i = 0; i < kChunk / 4; ++i) res_next[i] = src[i];
-        }
-      }
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccumStride;
-      // Two-deep software pipeline over the column chunks: the TMEM load (and residual load) of
-      // chunk j+2 is in flight while chunk j is converted and stored.
-      uint32_t acc_cur[kChunk], acc_next[kChunk];
+      uint32_t acc[kChunk];
       if (half < kNumChunks) {
-        if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + half * kChunk, acc_next);
-        else ptx::tmem_ld_32x16(taddr + half * kChunk, acc_next);
+        if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + half * kChunk, acc);
+        else ptx::tmem_ld_32x16(taddr + half * kChunk, acc);
       }
 #pragma unroll 1
       for (int j = half; j < kNumChunks; j += 2) {
+        const int n = n0 + j * kChunk;  // first absolute column of this chunk
+        const bool n_ok = n < p.N;
         ptx::tmem_ld_wait();
+        // ---- row-owner phase: registers -> swizzled staging buffer
+        if constexpr (kBf16Out) {
+          float v[kChunk];
 #pragma unroll
-        for (int i = 0; i < kChunk; ++i) acc_cur[i] = acc_next[i];
-        [[maybe_unused]] float4 res_cur[kChunk / 4];
-        if constexpr (kEpi == EPI_RESID_F32) {
+          for (int i = 0; i < kChunk; ++i) v[i] = __uint_as_float(acc[i]);
+          if (p.bias != nullptr && n_ok) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-          for (int i = 0; i < kChunk / 4; ++i) res_cur[i] = res_next[i];
-        }
-        const int jn = j + 2;
-        if (jn < kNumChunks) {
-          if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + jn * kChunk, acc_next);
-          else ptx::tmem_ld_32x16(taddr + jn * kChunk, acc_next);
-          if constexpr (kEpi == EPI_RESID_F32) {
-            if (row_ptr != nullptr && n0 + jn * kChunk < p.N) {
-              const float4* src = reinterpret_cast<const float4*>(static_cast<float*>(row_ptr) + n0 + jn * kChunk);
-#pragma unroll
-              for (int i = 0; i < kChunk / 4; ++i) res_next[i] = src[i];
+            for (int i = 0; i < kChunk / 4; ++i) {
+              const float4 t = __ldg(b4 + i);
+              v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
             }
           }
+          if constexpr (kEpi != EPI_STORE_BF16) {
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i) v[i] = gelu_fast(v[i]);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            uint4 q;
+            q.x = ptx::pack_bf16x2(v[8 * u + 0], v[8 * u + 1]);
+            q.y = ptx::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]);
+            q.z = ptx::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]);
+            q.w = ptx::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]);
+            stg[stage_unit<U>(lane, u)] = q;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            stg[stage_unit<U>(lane, u)] = make_uint4(acc[4 * u + 0], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
         }
-        const int n = n0 + j * kChunk;
-        if (row_ptr != nullptr && n < p.N) {
-          if constexpr (kEpi == EPI_RESID_F32) epilogue_resid<kChunk>(acc_cur, res_cur, p, n, row_ptr);
-          else epilogue_chunk<kEpi, kChunk>(acc_cur, p, n, row_ptr, pe_row);
+        // the accumulator registers are free again: fetch the next chunk while this one is written out
+        if (j + 2 < kNumChunks) {
+          if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + (j + 2) * kChunk, acc);
+          else ptx::tmem_ld_32x16(taddr + (j + 2) * kChunk, acc);
         }
+        __syncwarp();
+        // ---- transposed phase: each instruction covers 32/U rows x (16 U) contiguous bytes
+        constexpr int kRowsPerInstr = 32 / U;
+        const int u = lane % U;
+        const int rsub = lane / U;
+        if constexpr (kBf16Out) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int rr = i * kRowsPerInstr + rsub;
+            const int d = rowdst[rr];
+            const uint4 q = stg[stage_unit<U>(rr, u)];
+            if (d >= 0 && n_ok)
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + d * row_stride + n + 8 * u) = q;
+          }
+        } else {
+          const int nc = n + 4 * u;  // this lane's 4 columns
+          float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (kEpi != EPI_CONVOUT_PACK) {
+            if (p.bias != nullptr && n_ok) add = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
+          }
+          float4* dptr[U];
+          float4 old[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int rr = i * kRowsPerInstr + rsub;
+            const int d = rowdst[rr];
+            dptr[i] = (d >= 0 && n_ok) ? reinterpret_cast<float4*>(static_cast<float*>(p.out) + d * row_stride + nc) : nullptr;
+            if constexpr (kEpi == EPI_RESID_F32) {
+              if (dptr[i] != nullptr) old[i] = *dptr[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int rr = i * kRowsPerInstr + rsub;
+            const uint4 q = stg[stage_unit<U>(rr, u)];
+            float4 v = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+            if constexpr (kEpi == EPI_CONVOUT_PACK) {
+              const int m = m_blk * kBlockM + quarter * 32 + rr;
+              if (dptr[i] != nullptr) add = __ldg(reinterpret_cast<const float4*>(p.pe + static_cast<long long>(m % p.pe_period) * p.N + nc));
+            }
+            v.x += add.x; v.y += add.y; v.z += add.z; v.w += add.w;
+            if constexpr (kEpi == EPI_GELU_F32) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if constexpr (kEpi == EPI_RESID_F32) {
+              if (dptr[i] != nullptr) { v.x += old[i].x; v.y += old[i].y; v.z += old[i].z; v.w += old[i].w; }
+            }
+            if (dptr[i] != nullptr) *dptr[i] = v;
+          }
+        }
+        __syncwarp();  // staging buffer is rewritten by the next chunk
       }
       ptx::tc_fence_before();
       __syncwarp();
