@@ -24,9 +24,9 @@ inline PFN_tmapEncodeTiled get_tmap_encoder() {
   return fn;
 }
 
-// bf16 tensor, dims innermost-first, strides in BYTES for dims 1..rank-1, 128B swizzle, zero OOB fill.
-inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+// Tiled tensor map, dims innermost-first, strides in BYTES for dims 1..rank-1, zero OOB fill.
+inline bool make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle, std::string* err) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (enc == nullptr) {
     if (err) *err = "cuTensorMapEncodeTiled entry point not found";
@@ -42,14 +42,28 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const u
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
     return false;
   }
   return true;
+}
+
+inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+  return make_tmap(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   CU_TENSOR_MAP_SWIZZLE_128B, err);
+}
+
+// Row-major fp32 [rows, cols] OUTPUT matrix for the epilogue's TMA store / reduce: box {32 cols = 128 B, 32 rows}.
+inline bool make_tmap_out_f32(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t str[1] = {ld * 4};
+  uint32_t box[2] = {32, 32};
+  return make_tmap(out, base, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, err);
 }
 
 // Row-major [rows, cols] bf16 matrix (cols contiguous, leading dimension ld elements); box {64, box_rows}.
@@ -94,7 +108,7 @@ inline int gemm_num_sms() {
 
 template <int BLOCK_N, int kStages, int kAMode, int kEpi>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
-                               int max_ctas = 0) {
+                               const CUtensorMap* tout = nullptr, int max_ctas = 0) {
   using L = GemmSmem<BLOCK_N, kStages>;
   auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi>;
   static bool configured[64] = {};
@@ -111,7 +125,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, Gem
   int grid = gemm_num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, p);
   return cudaGetLastError();
 }
 

@@ -95,7 +95,7 @@ constexpr bool epi_is_bf16() {
 template <int BLOCK_N, int kStages, int kAMode, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using L = GemmSmem<BLOCK_N, kStages>;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert((L::kBBytes % 1024) == 0, "B stage must keep 1024-byte alignment");
@@ -106,13 +106,13 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * L::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint8_t* epi_base = smem + kStages * L::kStageBytes;  // 1024-byte aligned (TMA-store swizzle atoms)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + L::kEpiStageBytes + L::kEpiRowBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* epi_base = smem + kStages * L::kStageBytes + L::kBarrierBytes;  // 16-byte aligned
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +205,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------------ epilogue
     constexpr bool kBf16Out = epi_is_bf16<kEpi>();
+    // Dense fp32 outputs leave through the TMA: a plain tile store, or for the residual stream an
+    // in-L2 reduction (x += tile), so the SM never reads the old residual values.
+    constexpr bool kTmaOut = (kAMode == A_ROWS) && (kEpi == EPI_RESID_F32 || kEpi == EPI_STORE_F32);
     constexpr int U = kBf16Out ? kChunk / 8 : kChunk / 4;  // 16-byte units per staged row
     static_assert(kBf16Out || kChunk == 32, "fp32 epilogues assume 32-column chunks");
     const int ew = warp_idx - 4;
@@ -287,6 +290,25 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             q.w = ptx::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]);
             stg[stage_unit<U>(lane, u)] = q;
           }
+        } else if constexpr (kTmaOut) {
+          float v[kChunk];
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) v[i] = __uint_as_float(acc[i]);
+          if (p.bias != nullptr && n_ok) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int i = 0; i < kChunk / 4; ++i) {
+              const float4 t = __ldg(b4 + i);
+              v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+          // the previous chunk's bulk copy must have finished reading the staging buffer
+          if (lane == 0) ptx::bulk_wait_group_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            stg[stage_unit<U>(lane, u)] = make_uint4(__float_as_uint(v[4 * u + 0]), __float_as_uint(v[4 * u + 1]),
+                                                     __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
         } else {
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -296,6 +318,18 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (j + 2 < kNumChunks) {
           if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + (j + 2) * kChunk, acc);
           else ptx::tmem_ld_32x16(taddr + (j + 2) * kChunk, acc);
+        }
+        if constexpr (kTmaOut) {
+          // staging layout == SWIZZLE_128B box {32 cols, 32 rows}; rows beyond M are clipped by the tensor map
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && n_ok) {
+            const int row0 = m_blk * kBlockM + quarter * 32;
+            if constexpr (kEpi == EPI_RESID_F32) ptx::tma_reduce_add_2d(&tmap_out, stg, n, row0);
+            else ptx::tma_store_2d(&tmap_out, stg, n, row0);
+            ptx::bulk_commit_group();
+          }
+          continue;
         }
         __syncwarp();
         // ---- transposed phase: each instruction covers 32/U rows x (16 U) contiguous bytes
@@ -351,6 +385,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if constexpr (kTmaOut) {
+      if (lane == 0) ptx::bulk_wait_group_read<0>();  // smem must outlive the last bulk copies
     }
   }
 

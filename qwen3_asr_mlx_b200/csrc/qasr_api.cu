@@ -103,11 +103,27 @@ struct qasr_handle {
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
   qasr_profile prof_acc{};
-  // pinned staging for tables
-  void* pin = nullptr;
-  size_t pin_bytes = 0;
+  // pinned staging arena for the per-call tables (bump-allocated; one event guards reuse)
+  uint8_t* pin = nullptr;
+  size_t pin_bytes = 0, pin_cur = 0;
   cudaEvent_t pin_event = nullptr;
   bool pin_event_pending = false;
+  // CUDA-graph replay of whole calls (keyed by entry point, pointers, dtype and offsets)
+  bool use_graphs = true;
+  bool capturing = false;
+  struct GraphEntry {
+    uint64_t key = 0;
+    cudaGraphExec_t exec = nullptr;
+    uint8_t* pin = nullptr;  // this graph's own table staging (memcpy nodes read it at every replay)
+    std::vector<long long> token_offsets;
+    uint64_t launches = 0;   // kernels per replay (for stats)
+    uint64_t last_use = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  std::map<uint64_t, std::pair<int, size_t>> seen;  // key -> (times seen, pinned bytes the eager run used)
+  uint64_t use_clock = 0;
+  cudaStream_t own_stream = nullptr;  // used when the caller passes the legacy NULL stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -147,8 +163,12 @@ struct ProfScope {
   ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
 };
 
+void invalidate_graphs(qasr_handle* h);
+
 int dev_alloc(qasr_handle* h, DevBuf& b, size_t bytes, bool zero) {
   if (bytes <= b.bytes) return QASR_OK;
+  if (h->capturing) return fail(h, QASR_ERR_STATE, "workspace growth during graph capture");
+  invalidate_graphs(h);  // captured graphs hold the old pointers
   if (b.p) {
     QCUDA(h, cudaFree(b.p));
     h->stats.workspace_bytes -= b.bytes;
@@ -342,18 +362,49 @@ int ensure_workspace(qasr_handle* h, long long tokens, long long chunks, long lo
   return QASR_OK;
 }
 
-int ensure_pinned(qasr_handle* h, size_t bytes) {
-  if (h->pin_event_pending) {  // previous call's table upload must have drained before we overwrite
+void invalidate_graphs(qasr_handle* h) {
+  for (auto& g : h->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.pin) cudaFreeHost(g.pin);
+  }
+  h->graphs.clear();
+  h->seen.clear();
+}
+
+// Start of an eager API call: wait until the previous call's table uploads have drained, then
+// make sure the arena can hold `bytes`.
+int pin_begin(qasr_handle* h, size_t bytes) {
+  if (h->capturing) { h->pin_cur = 0; return QASR_OK; }  // the graph entry's own buffer is installed
+  if (h->pin_event_pending) {
     QCUDA(h, cudaEventSynchronize(h->pin_event));
     h->pin_event_pending = false;
   }
+  h->pin_cur = 0;
   if (bytes <= h->pin_bytes) return QASR_OK;
   if (h->pin) cudaFreeHost(h->pin);
   h->pin = nullptr;
   h->pin_bytes = 0;
-  QCUDA(h, cudaMallocHost(&h->pin, bytes));
+  void* p = nullptr;
+  QCUDA(h, cudaMallocHost(&p, bytes));
+  h->pin = static_cast<uint8_t*>(p);
   h->pin_bytes = bytes;
   return QASR_OK;
+}
+uint8_t* pin_take(qasr_handle* h, size_t bytes) {
+  const size_t at = (h->pin_cur + 15) & ~static_cast<size_t>(15);
+  if (at + bytes > h->pin_bytes) return nullptr;
+  h->pin_cur = at + bytes;
+  return h->pin + at;
+}
+int pin_end(qasr_handle* h, cudaStream_t st) {
+  if (h->capturing) return QASR_OK;
+  QCUDA(h, cudaEventRecord(h->pin_event, st));
+  h->pin_event_pending = true;
+  return QASR_OK;
+}
+size_t pin_bytes_for(long long batch, long long chunks, long long windows) {
+  return static_cast<size_t>(batch + 1) * 20 + static_cast<size_t>(chunks) * (sizeof(ChunkDesc) + kTokensPerChunk * sizeof(int)) +
+         static_cast<size_t>(windows) * sizeof(WindowDesc) + 256;
 }
 
 template <int VPL>
@@ -381,8 +432,15 @@ template <int EPI>
 int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, void* out,
           long long ldo, const float* bias, cudaStream_t st) {
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
+  CUtensorMap tout;
+  const CUtensorMap* toutp = nullptr;
+  if (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {  // fp32 outputs leave through a TMA store / reduce (exact row count: rows >= M are clipped)
+    std::string e;
+    if (!make_tmap_out_f32(&tout, out, M, N, ldo, &e)) return fail(h, QASR_ERR_CUDA, e);
+    toutp = &tout;
+  }
   ProfScope ps(h, cat, st, 2.0 * M * N * K, 0.0);
-  QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI>(ta, tw, p, st)));
+  QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI>(ta, tw, p, st, toutp)));
   return QASR_OK;
 }
 
@@ -411,16 +469,14 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
   int rc;
   if ((rc = ensure_workspace(h, 0, 0, 0, B))) return rc;
   const size_t b8 = static_cast<size_t>(B + 1) * 8, b4 = static_cast<size_t>(B + 1) * 4;
-  if ((rc = ensure_pinned(h, 2 * b8 + b4))) return rc;
-  uint8_t* pin = static_cast<uint8_t*>(h->pin);
+  uint8_t* pin = pin_take(h, 2 * b8 + b4);
+  if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
   memcpy(pin, soffs.data(), b8);
   memcpy(pin + b8, foffs.data(), b8);
   memcpy(pin + 2 * b8, boffs.data(), b4);
   QCUDA(h, cudaMemcpyAsync(h->d_soffs.p, pin, b8, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_foffs.p, pin + b8, b8, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_boffs.p, pin + 2 * b8, b4, cudaMemcpyHostToDevice, st));
-  QCUDA(h, cudaEventRecord(h->pin_event, st));
-  h->pin_event_pending = true;
   QCUDA(h, cudaMemsetAsync(h->d_uttmax.p, 0, static_cast<size_t>(B) * 4, st));
 
   MelTables tab{h->d_window, h->d_twiddle, h->d_fb_start, h->d_fb_count, h->d_fb_weight};
@@ -484,16 +540,14 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   int rc;
   if ((rc = ensure_workspace(h, n, nchunks, nwin, B))) return rc;
   const size_t bc = chunks.size() * sizeof(ChunkDesc), br = rowmap.size() * sizeof(int), bw = windows.size() * sizeof(WindowDesc);
-  if ((rc = ensure_pinned(h, bc + br + bw))) return rc;
-  uint8_t* pin = static_cast<uint8_t*>(h->pin);
+  uint8_t* pin = pin_take(h, bc + br + bw);
+  if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
   memcpy(pin, chunks.data(), bc);
   memcpy(pin + bc, rowmap.data(), br);
   memcpy(pin + bc + br, windows.data(), bw);
   QCUDA(h, cudaMemcpyAsync(h->d_chunks.p, pin, bc, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_rowmap.p, pin + bc, br, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_windows.p, pin + bc + br, bw, cudaMemcpyHostToDevice, st));
-  QCUDA(h, cudaEventRecord(h->pin_event, st));
-  h->pin_event_pending = true;
 
   float* x = static_cast<float*>(h->x.p);
   __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(h->xn.p);
@@ -634,7 +688,14 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
     const int v = atoi(sg);
     if (v > 0) h->stem_group = v;
   }
-  if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaEventCreate failed"); }
+  if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
+  if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, QASR_ERR_CUDA, "stream / event creation failed");
+  }
   rc = init_mel_tables(h);
   if (rc) { g_last_error = h->err; qasr_destroy(h); return rc; }
   *out = h;
@@ -652,8 +713,12 @@ void qasr_destroy(qasr_handle* h) {
   for (DevBuf* b : bufs) dev_free(h, *b);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+  invalidate_graphs(h);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_event) cudaEventDestroy(h->pin_event);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
 
@@ -769,66 +834,219 @@ int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch) {
   return QASR_OK;
 }
 
-int qasr_mel(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, float* mel_dev, void* stream) {
-  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+// ---------------------------------------------------------------------------------- call dispatch
+// Every device-pointer entry point funnels through dispatch(): the first call with a given
+// (entry, pointers, dtype, offsets) runs eagerly; the second is captured into a CUDA graph (its
+// own pinned table staging included) and from then on the whole call is one cudaGraphLaunch.
+namespace {
+
+enum CallKind : int { CALL_MEL = 1, CALL_ENCODE = 2, CALL_ENCODE_AUDIO = 3 };
+struct CallArgs {
+  int kind;
+  const float* in;
+  void* out;
+  const int64_t* offs;
+  int B;
+  int out_dtype;
+  int64_t* toffs_out;
+};
+
+uint64_t fnv1a(uint64_t hsh, const void* data, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(data);
+  for (size_t i = 0; i < n; ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+  return hsh;
+}
+uint64_t call_key(const CallArgs& c) {
+  uint64_t k = 1469598103934665603ull;
+  k = fnv1a(k, &c.kind, sizeof(c.kind));
+  k = fnv1a(k, &c.in, sizeof(c.in));
+  k = fnv1a(k, &c.out, sizeof(c.out));
+  k = fnv1a(k, &c.out_dtype, sizeof(c.out_dtype));
+  k = fnv1a(k, &c.B, sizeof(c.B));
+  return fnv1a(k, c.offs, sizeof(int64_t) * (static_cast<size_t>(c.B) + 1));
+}
+
+int call_body(qasr_handle* h, const CallArgs& c, cudaStream_t st) {
+  int rc;
+  if (c.kind == CALL_MEL) return mel_impl(h, c.in, c.offs, c.B, static_cast<float*>(c.out), nullptr, st);
+  if (c.kind == CALL_ENCODE) {
+    std::vector<long long> fo(c.offs, c.offs + c.B + 1);
+    return encode_impl(h, c.in, fo.data(), c.B, c.out, c.out_dtype, c.toffs_out, st);
+  }
+  std::vector<long long> foffs;
+  if ((rc = mel_impl(h, c.in, c.offs, c.B, static_cast<float*>(h->mel_scratch.p), &foffs, st))) return rc;
+  return encode_impl(h, static_cast<const float*>(h->mel_scratch.p), foffs.data(), c.B, c.out, c.out_dtype, c.toffs_out, st);
+}
+
+// Upper bound of the pinned table bytes one call needs, plus scratch sizing for the fused entry.
+int call_prepare(qasr_handle* h, const CallArgs& c, size_t* pin_bytes) {
+  long long frames = 0;
+  for (int u = 0; u < c.B; ++u) {
+    const long long d = c.offs[u + 1] - c.offs[u];
+    if (d < 0) return fail(h, QASR_ERR_INVALID, "offsets must be non-decreasing");
+    frames += (c.kind == CALL_ENCODE) ? d : d / kMelHop;
+  }
+  const long long chunks = frames / kChunkFrames + c.B;
+  const long long windows = chunks * kTokensPerChunk / window_tokens(h->cfg) + c.B;
+  *pin_bytes = 2 * pin_bytes_for(c.B, chunks, windows);
+  if (c.kind == CALL_ENCODE_AUDIO && frames > h->cap_mel_frames) {
+    int rc;
+    if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(frames) * kMelBins * 4, false))) return rc;
+    h->cap_mel_frames = frames;
+  }
+  return QASR_OK;
+}
+
+int dispatch(qasr_handle* h, const CallArgs& c, cudaStream_t user_stream) {
   int rc;
   if ((rc = check_device(h))) return rc;
-  return mel_impl(h, audio_dev, sample_offsets, batch, mel_dev, nullptr, static_cast<cudaStream_t>(stream));
+  if (!c.in || !c.out || !c.offs || c.B <= 0) return fail(h, QASR_ERR_INVALID, "bad argument (null pointer or empty batch)");
+  // The legacy NULL stream cannot be captured: run on a private stream, ordered after / before it by events.
+  cudaStream_t st = user_stream;
+  const bool redirect = (user_stream == nullptr || user_stream == cudaStreamLegacy);
+  if (redirect) {
+    QCUDA(h, cudaEventRecord(h->ev_in, user_stream));
+    QCUDA(h, cudaStreamWaitEvent(h->own_stream, h->ev_in, 0));
+    st = h->own_stream;
+  }
+  const bool graphs_ok = h->use_graphs && !h->profile && !h->debug;
+  const uint64_t key = call_key(c);
+  bool done = false;
+  if (graphs_ok) {
+    for (auto& g : h->graphs) {
+      if (g.key != key) continue;
+      QCUDA(h, cudaGraphLaunch(g.exec, st));
+      if (c.toffs_out)
+        for (size_t i = 0; i < g.token_offsets.size(); ++i) c.toffs_out[i] = g.token_offsets[i];
+      h->stats.kernel_launches += g.launches;
+      g.last_use = ++h->use_clock;
+      done = true;
+      break;
+    }
+  }
+  if (!done) {
+    size_t pin_need = 0;
+    if ((rc = call_prepare(h, c, &pin_need))) return rc;
+    auto seen_it = h->seen.find(key);
+    const bool try_capture = graphs_ok && seen_it != h->seen.end() && seen_it->second.first >= 1;
+    if (try_capture) {
+      qasr_handle::GraphEntry ge;
+      ge.key = key;
+      const size_t bytes = seen_it->second.second + 256;
+      void* pp = nullptr;
+      QCUDA(h, cudaMallocHost(&pp, bytes));
+      ge.pin = static_cast<uint8_t*>(pp);
+      uint8_t* save_pin = h->pin;
+      const size_t save_bytes = h->pin_bytes, save_cur = h->pin_cur;
+      h->pin = ge.pin; h->pin_bytes = bytes; h->pin_cur = 0;
+      h->capturing = true;
+      const uint64_t launches0 = h->stats.kernel_launches;
+      cudaError_t e1 = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      rc = (e1 == cudaSuccess) ? call_body(h, c, st) : QASR_ERR_CUDA;
+      cudaGraph_t graph = nullptr;
+      cudaError_t e2 = (e1 == cudaSuccess) ? cudaStreamEndCapture(st, &graph) : e1;
+      h->capturing = false;
+      h->pin = save_pin; h->pin_bytes = save_bytes; h->pin_cur = save_cur;
+      ge.launches = h->stats.kernel_launches - launches0;
+      cudaError_t e3 = cudaErrorUnknown;
+      if (rc == QASR_OK && e2 == cudaSuccess && graph) e3 = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e3 == cudaSuccess) {
+        if (c.toffs_out && c.kind != CALL_MEL) ge.token_offsets.assign(c.toffs_out, c.toffs_out + c.B + 1);
+        ge.last_use = ++h->use_clock;
+        if (h->graphs.size() >= 8) {  // evict the least recently used graph
+          size_t victim = 0;
+          for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+          cudaGraphExecDestroy(h->graphs[victim].exec);
+          cudaFreeHost(h->graphs[victim].pin);
+          h->graphs.erase(h->graphs.begin() + victim);
+        }
+        h->graphs.push_back(ge);
+        QCUDA(h, cudaGraphLaunch(ge.exec, st));
+        done = true;
+      } else {
+        cudaGetLastError();  // clear; this call shape is not capturable: stay eager for it
+        cudaFreeHost(ge.pin);
+        h->stats.kernel_launches = launches0;
+        seen_it->second.first = -(1 << 30);
+        if (rc != QASR_OK && rc != QASR_ERR_CUDA) return rc;  // argument errors surface as such
+      }
+    }
+    if (!done) {
+      if ((rc = pin_begin(h, pin_need))) return rc;
+      if ((rc = call_body(h, c, st))) return rc;
+      auto& sn = h->seen[key];
+      sn.first += 1;
+      sn.second = h->pin_cur;
+      if (h->seen.size() > 4096) h->seen.clear();
+      if ((rc = pin_end(h, st))) return rc;
+    }
+  }
+  if (redirect) {
+    QCUDA(h, cudaEventRecord(h->ev_out, h->own_stream));
+    QCUDA(h, cudaStreamWaitEvent(user_stream, h->ev_out, 0));
+  }
+  return QASR_OK;
+}
+
+}  // namespace
+
+int qasr_mel(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, float* mel_dev, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  CallArgs c{CALL_MEL, audio_dev, mel_dev, sample_offsets, batch, QASR_F32, nullptr};
+  return dispatch(h, c, static_cast<cudaStream_t>(stream));
 }
 
 int qasr_encode(qasr_handle* h, const float* mel_dev, const int64_t* frame_offsets, int32_t batch, void* emb_dev,
                 int out_dtype, int64_t* token_offsets_out, void* stream) {
   if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
-  int rc;
-  if ((rc = check_device(h))) return rc;
-  if (!frame_offsets || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
-  std::vector<long long> fo(frame_offsets, frame_offsets + batch + 1);
-  return encode_impl(h, mel_dev, fo.data(), batch, emb_dev, out_dtype, token_offsets_out, static_cast<cudaStream_t>(stream));
+  CallArgs c{CALL_ENCODE, mel_dev, emb_dev, frame_offsets, batch, out_dtype, token_offsets_out};
+  return dispatch(h, c, static_cast<cudaStream_t>(stream));
 }
 
 int qasr_encode_audio(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, void* emb_dev,
                       int out_dtype, int64_t* token_offsets_out, void* stream) {
   if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  CallArgs c{CALL_ENCODE_AUDIO, audio_dev, emb_dev, sample_offsets, batch, out_dtype, token_offsets_out};
+  return dispatch(h, c, static_cast<cudaStream_t>(stream));
+}
+
+// Host-pointer flavours: H2D, the device entry point, D2H, all on the handle's private stream.
+namespace {
+int host_call(qasr_handle* h, int kind, const float* in_host, size_t in_bytes, const int64_t* offs, int32_t batch,
+              void* out_host, size_t out_bytes, int out_dtype, int64_t* toffs_out) {
   int rc;
   if ((rc = check_device(h))) return rc;
-  if (!sample_offsets || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_audio: bad argument");
-  long long total_frames = 0;
-  for (int u = 0; u < batch; ++u) total_frames += (sample_offsets[u + 1] - sample_offsets[u]) / kMelHop;
-  if (total_frames <= 0) return fail(h, QASR_ERR_INVALID, "no frames");
-  if (total_frames > h->cap_mel_frames) {
-    if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(total_frames) * kMelBins * 4, false))) return rc;
-    h->cap_mel_frames = total_frames;
-  }
-  std::vector<long long> foffs;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((rc = mel_impl(h, audio_dev, sample_offsets, batch, static_cast<float*>(h->mel_scratch.p), &foffs, st))) return rc;
-  return encode_impl(h, static_cast<const float*>(h->mel_scratch.p), foffs.data(), batch, emb_dev, out_dtype, token_offsets_out, st);
+  if ((rc = dev_alloc(h, h->io_in, in_bytes, false))) return rc;
+  if ((rc = dev_alloc(h, h->io_out, out_bytes, false))) return rc;
+  cudaStream_t st = h->own_stream;
+  QCUDA(h, cudaMemcpyAsync(h->io_in.p, in_host, in_bytes, cudaMemcpyHostToDevice, st));
+  CallArgs c{kind, static_cast<const float*>(h->io_in.p), h->io_out.p, offs, batch, out_dtype, toffs_out};
+  if ((rc = dispatch(h, c, st))) return rc;
+  QCUDA(h, cudaMemcpyAsync(out_host, h->io_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  QCUDA(h, cudaStreamSynchronize(st));
+  return QASR_OK;
 }
+}  // namespace
 
 int qasr_mel_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch, float* mel_host) {
   if (!h || !audio_host || !sample_offsets || !mel_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_mel_host: bad argument");
-  int rc;
-  if ((rc = check_device(h))) return rc;
   const long long ns = sample_offsets[batch];
   long long nf = 0;
-  for (int u = 0; u < batch; ++u) nf += (sample_offsets[u + 1] - sample_offsets[u]) / kMelHop;
-  if (ns <= 0 || nf <= 0) return fail(h, QASR_ERR_INVALID, "need >= 160 samples per utterance");
-  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(ns) * 4, false))) return rc;
-  if ((rc = dev_alloc(h, h->io_out, static_cast<size_t>(nf) * kMelBins * 4, false))) return rc;
-  QCUDA(h, cudaMemcpyAsync(h->io_in.p, audio_host, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, 0));
-  if ((rc = mel_impl(h, static_cast<const float*>(h->io_in.p), sample_offsets, batch, static_cast<float*>(h->io_out.p), nullptr, 0))) return rc;
-  QCUDA(h, cudaMemcpyAsync(mel_host, h->io_out.p, static_cast<size_t>(nf) * kMelBins * 4, cudaMemcpyDeviceToHost, 0));
-  QCUDA(h, cudaStreamSynchronize(0));
-  return QASR_OK;
+  for (int u = 0; u < batch; ++u) {
+    if (sample_offsets[u + 1] - sample_offsets[u] < kMelHop) return fail(h, QASR_ERR_INVALID, "need >= 160 samples per utterance");
+    nf += (sample_offsets[u + 1] - sample_offsets[u]) / kMelHop;
+  }
+  return host_call(h, CALL_MEL, audio_host, static_cast<size_t>(ns) * 4, sample_offsets, batch, mel_host,
+                   static_cast<size_t>(nf) * kMelBins * 4, QASR_F32, nullptr);
 }
 
 int qasr_encode_host(qasr_handle* h, const float* mel_host, const int64_t* frame_offsets, int32_t batch, void* emb_host,
                      int out_dtype, int64_t* token_offsets_out) {
   if (!h || !mel_host || !frame_offsets || !emb_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_host: bad argument");
-  int rc;
-  if ((rc = check_device(h))) return rc;
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
   const long long nf = frame_offsets[batch];
-  if (nf <= 0) return fail(h, QASR_ERR_INVALID, "no frames");
   long long ntok = 0;
   for (int u = 0; u < batch; ++u) {
     int64_t t = 0;
@@ -837,22 +1055,14 @@ int qasr_encode_host(qasr_handle* h, const float* mel_host, const int64_t* frame
     ntok += t;
   }
   const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
-  const size_t out_bytes = static_cast<size_t>(ntok) * h->cfg.output_dim * esz;
-  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(nf) * kMelBins * 4, false))) return rc;
-  if ((rc = dev_alloc(h, h->io_out, out_bytes, false))) return rc;
-  QCUDA(h, cudaMemcpyAsync(h->io_in.p, mel_host, static_cast<size_t>(nf) * kMelBins * 4, cudaMemcpyHostToDevice, 0));
-  std::vector<long long> fo(frame_offsets, frame_offsets + batch + 1);
-  if ((rc = encode_impl(h, static_cast<const float*>(h->io_in.p), fo.data(), batch, h->io_out.p, out_dtype, token_offsets_out, 0))) return rc;
-  QCUDA(h, cudaMemcpyAsync(emb_host, h->io_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
-  QCUDA(h, cudaStreamSynchronize(0));
-  return QASR_OK;
+  return host_call(h, CALL_ENCODE, mel_host, static_cast<size_t>(nf) * kMelBins * 4, frame_offsets, batch, emb_host,
+                   static_cast<size_t>(ntok) * h->cfg.output_dim * esz, out_dtype, token_offsets_out);
 }
 
 int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
                            void* emb_host, int out_dtype, int64_t* token_offsets_out) {
   if (!h || !audio_host || !sample_offsets || !emb_host || batch <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode_audio_host: bad argument");
-  int rc;
-  if ((rc = check_device(h))) return rc;
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
   const long long ns = sample_offsets[batch];
   long long ntok = 0;
   for (int u = 0; u < batch; ++u) {
@@ -863,14 +1073,8 @@ int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_
     ntok += t;
   }
   const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
-  const size_t out_bytes = static_cast<size_t>(ntok) * h->cfg.output_dim * esz;
-  if ((rc = dev_alloc(h, h->io_in, static_cast<size_t>(ns) * 4, false))) return rc;
-  if ((rc = dev_alloc(h, h->io_out, out_bytes, false))) return rc;
-  QCUDA(h, cudaMemcpyAsync(h->io_in.p, audio_host, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, 0));
-  if ((rc = qasr_encode_audio(h, static_cast<const float*>(h->io_in.p), sample_offsets, batch, h->io_out.p, out_dtype, token_offsets_out, nullptr))) return rc;
-  QCUDA(h, cudaMemcpyAsync(emb_host, h->io_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
-  QCUDA(h, cudaStreamSynchronize(0));
-  return QASR_OK;
+  return host_call(h, CALL_ENCODE_AUDIO, audio_host, static_cast<size_t>(ns) * 4, sample_offsets, batch, emb_host,
+                   static_cast<size_t>(ntok) * h->cfg.output_dim * esz, out_dtype, token_offsets_out);
 }
 
 int qasr_mel_filterbank(float* out) {
@@ -968,6 +1172,7 @@ int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float
   QCUDA(h, cudaMalloc(&da, static_cast<size_t>(M) * K * 2));
   QCUDA(h, cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
   QCUDA(h, cudaMalloc(&dout, static_cast<size_t>(M) * N * 4));
+  if (mode == 2) QCUDA(h, cudaMemcpy(dout, out, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
   QCUDA(h, cudaMemcpy(da, a, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
   QCUDA(h, cudaMemcpy(dw, w, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
   if (bias) {
@@ -978,8 +1183,12 @@ int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float
   std::string e;
   if (!make_tmap_rows(&ta, da, M, K, K, kBlockM, &e) || !make_tmap_rows(&tw, dw, N, K, K, 256, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
   GemmParams p = dense_params(M, N, K, dout, N, static_cast<const float*>(db));
+  CUtensorMap tout;
+  if (!make_tmap_out_f32(&tout, dout, M, N, N, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
   if (mode == 1) QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_GELU_F32>(ta, tw, p, 0)));
-  else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_STORE_F32>(ta, tw, p, 0)));
+  else if (mode == 2) {  // residual mode: out is pre-filled by the caller (bias vector replicated) and accumulated into
+    QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_RESID_F32>(ta, tw, p, 0, &tout)));
+  } else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_STORE_F32>(ta, tw, p, 0, &tout)));
   QCUDA(h, cudaDeviceSynchronize());
   QCUDA(h, cudaMemcpy(out, dout, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(dw); cudaFree(dout);

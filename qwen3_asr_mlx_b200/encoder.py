@@ -167,14 +167,21 @@ class AudioEncoder:
                     packed[int(s):int(e)].copy_(as_device_f32(w, h.torch_device))
             return self.encode_packed_audio(packed, soffs, out_dtype)
 
-    def encode_packed_audio(self, packed_audio: torch.Tensor, soffs: np.ndarray, out_dtype: str = "float32") -> Tuple[DeviceArray, np.ndarray]:
-        """Device-resident packed audio (float32, ``soffs`` sample offsets) -> packed embeddings."""
+    def encode_packed_audio(self, packed_audio: torch.Tensor, soffs: np.ndarray, out_dtype: str = "float32",
+                            out: Optional[torch.Tensor] = None) -> Tuple[DeviceArray, np.ndarray]:
+        """Device-resident packed audio (float32, ``soffs`` sample offsets) -> packed embeddings.
+
+        Passing the same ``packed_audio`` / ``out`` buffers and offsets again replays the CUDA graph
+        libqasr captured for that call instead of re-launching ~230 kernels."""
         self._ensure_weights()
         h = self._handle
         B = len(soffs) - 1
         n_tok = sum(self.num_tokens(int(soffs[u + 1] - soffs[u]) // HOP_LENGTH) for u in range(B))
         tdt, cdt = (torch.bfloat16, _lib.QASR_BF16) if out_dtype in ("bfloat16", "bf16") else (torch.float32, _lib.QASR_F32)
-        out = torch.empty((n_tok, self.config.output_dim), dtype=tdt, device=h.torch_device)
+        if out is None:
+            out = torch.empty((n_tok, self.config.output_dim), dtype=tdt, device=h.torch_device)
+        elif tuple(out.shape) != (n_tok, self.config.output_dim) or out.dtype != tdt or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {tdt} tensor of shape {(n_tok, self.config.output_dim)}")
         toffs = np.zeros(B + 1, dtype=np.int64)
         h.check(h.lib.qasr_encode_audio(h.ptr, ctypes.c_void_p(packed_audio.data_ptr()), runtime.i64_ptr(soffs), B,
                                         ctypes.c_void_p(out.data_ptr()), cdt, runtime.i64_ptr(toffs), h.stream_ptr()))

@@ -59,6 +59,11 @@ def test_tcgen05_gemm_kernel(shape):
     _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 0, out.ctypes.data_as(f32)))
     ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
     assert np.abs(out - ref).max() <= 1e-4  # fp32 accumulation of exact bf16 products
+    # residual epilogue (TMA reduce-add into an fp32 matrix that already holds values)
+    resid = rng.standard_normal((M, N)).astype(np.float32)
+    acc = resid.copy()
+    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 2, acc.ctypes.data_as(f32)))
+    assert np.abs(acc - (ref + resid)).max() <= 1e-4
 
 
 @pytest.mark.parametrize("n_samples", [160, 16000, 16000 * 4 + 7000, 16000 * 9 + 4321, 16000 * 20 + 333])
