@@ -140,7 +140,7 @@ int qasr_set_debug(qasr_handle* h, int enabled);
  *       "hidden" (fp32 [n_tok, d_model] after the last layer, before ln_post). */
 int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_floats);
 /* Stand-alone dense GEMM through the encoder's tcgen05 kernel: out[M,N] = a[M,K] * w[N,K]^T (+bias),
- * a/w bf16 HOST arrays, out fp32 HOST array.  mode: 0 store, 1 gelu, 2 residual (out += result, out is also an input). */
+ * a/w bf16 HOST arrays, out fp32 HOST array.  mode: 0 store, 1 gelu, 2 residual (out += result, out is also an input); +16 selects the CTA-pair (cta_group::2) kernel. */
 int qasr_test_gemm(int device, const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, int32_t M,
                    int32_t N, int32_t K, int32_t mode, float* out);
 

@@ -106,11 +106,11 @@ inline int gemm_num_sms() {
   return v;
 }
 
-template <int BLOCK_N, int kStages, int kAMode, int kEpi>
+template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
                                const CUtensorMap* tout = nullptr, int max_ctas = 0) {
-  using L = GemmSmem<BLOCK_N, kStages>;
-  auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi>;
+  using L = GemmSmem<BLOCK_N, kStages, kCta>;
+  auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi, kCta>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -120,13 +120,30 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, Gem
     configured[dev & 63] = true;
   }
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = ((p.num_m_tiles + kCta - 1) / kCta) * p.num_n_tiles;  // tiles of kCta x 128 rows
   if (tiles <= 0 || p.num_k_blocks <= 0) return cudaSuccess;
   int grid = gemm_num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (tiles < grid) grid = tiles;
-  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, p);
-  return cudaGetLastError();
+  grid = (grid / kCta) * kCta;
+  if (tiles * kCta < grid) grid = tiles * kCta;
+  if constexpr (kCta == 1) {
+    kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, p);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, p);
+  }
 }
 
 // Plain dense GEMM parameter block: A [M,K] row-major, W [N,K] row-major.

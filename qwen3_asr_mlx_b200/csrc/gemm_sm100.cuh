@@ -69,10 +69,12 @@ struct GemmParams {
   int pe_period;
 };
 
-template <int BLOCK_N, int kStages>
+// kCta = 2: a pair of CTAs (thread-block cluster of 2, one per SM of a TPC) computes a 256 x BLOCK_N
+// tile with tcgen05.mma.cta_group::2; each CTA stages its own 128 A rows and HALF of the B rows.
+template <int BLOCK_N, int kStages, int kCta = 1>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / kCta) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kEpiStageBytes = 8 * 32 * 32 * 4;  // 8 epilogue warps x (32 rows x 128 B)
@@ -92,11 +94,12 @@ constexpr bool epi_is_bf16() {
   return kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT;
 }
 
-template <int BLOCK_N, int kStages, int kAMode, int kEpi>
+template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-  using L = GemmSmem<BLOCK_N, kStages>;
+  using L = GemmSmem<BLOCK_N, kStages, kCta>;
+  static_assert(kCta == 1 || kCta == 2, "cta_group must be 1 or 2");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert((L::kBBytes % 1024) == 0, "B stage must keep 1024-byte alignment");
   constexpr int kChunk = (BLOCK_N % 32 == 0) ? 32 : 16;  // epilogue column granularity
@@ -116,7 +119,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // Tile scheduler: a "tile" is kCta vertically adjacent 128-row blocks x one BLOCK_N column block.
+  const uint32_t cta_rank = (kCta == 2) ? ptx::cluster_ctarank() : 0u;
+  const int sched_id = static_cast<int>(blockIdx.x) / kCta;
+  const int sched_n = static_cast<int>(gridDim.x) / kCta;
+  const int num_tiles = ((p.num_m_tiles + kCta - 1) / kCta) * p.num_n_tiles;
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -129,16 +136,17 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+      ptx::mbar_init(&tmem_empty_bar[i], kNumEpiWarps * kCta);  // the leader collects both CTAs' epilogue warps
     }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 2) {
-    ptx::tmem_alloc<1>(tmem_ptr_smem, 2 * kAccumStride);
-    ptx::tmem_relinquish<1>();
+    ptx::tmem_alloc<kCta>(tmem_ptr_smem, 2 * kAccumStride);
+    ptx::tmem_relinquish<kCta>();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote signals
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -149,25 +157,44 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = 0;
       // a conv box covers rows_per_tile * OW (< 128) pixels: the tail rows of the stage are never written
       const uint32_t a_tx = p.a_tx_bytes > 0 ? static_cast<uint32_t>(p.a_tx_bytes) : static_cast<uint32_t>(L::kABytes);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles;
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+        const int m_blk = (tile / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
         const int n_blk = tile % p.num_n_tiles;
+        const int b_row0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / kCta);  // this CTA's B rows
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], a_tx + L::kBBytes);
           void* sa = smem_a + stage * L::kABytes;
           void* sb = smem_b + stage * L::kBBytes;
-          if constexpr (kAMode == A_ROWS) {
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
+          if constexpr (kCta == 1) {
+            ptx::mbar_expect_tx(&full_bar[stage], a_tx + L::kBBytes);
+            if constexpr (kAMode == A_ROWS) {
+              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+              ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, b_row0);
+            } else {
+              const int tap = kb / p.conv_kc_per_tap;
+              const int kc = kb - tap * p.conv_kc_per_tap;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const int plane = 2 * (kh != 1) + (kw != 1);
+              const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
+              ptx::tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * kBlockK, (kw != 0), row0, plane);
+              ptx::tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBlockK, tap, b_row0);
+            }
           } else {
-            const int tap = kb / p.conv_kc_per_tap;
-            const int kc = kb - tap * p.conv_kc_per_tap;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const int plane = 2 * (kh != 1) + (kw != 1);
-            const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
-            ptx::tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * kBlockK, (kw != 0), row0, plane);
-            ptx::tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBlockK, tap, n_blk * BLOCK_N);
+            // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the pair
+            const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (a_tx + L::kBBytes));
+            if constexpr (kAMode == A_ROWS) {
+              ptx::tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * kBlockK, m_blk * kBlockM);
+              ptx::tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * kBlockK, b_row0);
+            } else {
+              const int tap = kb / p.conv_kc_per_tap;
+              const int kc = kb - tap * p.conv_kc_per_tap;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const int plane = 2 * (kh != 1) + (kw != 1);
+              const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
+              ptx::tma_load_4d_cg2(sa, &tmap_a, lead_bar, kc * kBlockK, (kw != 0), row0, plane);
+              ptx::tma_load_3d_cg2(sb, &tmap_b, lead_bar, kc * kBlockK, tap, b_row0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -175,13 +202,13 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {  // with cta_group::2 only the leader CTA issues the pair's MMAs
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM * kCta, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccumStride;
@@ -193,12 +220,16 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-            ptx::umma_bf16_ss<1>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kCta == 1) ptx::umma_commit(&empty_bar[stage]);
+          else ptx::umma_commit_cg2(&empty_bar[stage], 0x3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (kCta == 1) ptx::umma_commit(&tmem_full_bar[as]);
+        else ptx::umma_commit_cg2(&tmem_full_bar[as], 0x3);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -219,8 +250,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const long long row_stride = (kAMode == A_ROWS) ? p.ldo : static_cast<long long>(p.out_C);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_tiles;
+    for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+      const int m_blk = (tile / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
       const int n_blk = tile % p.num_n_tiles;
       const int n0 = n_blk * BLOCK_N;
 
@@ -323,8 +354,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           // staging layout == SWIZZLE_128B box {32 cols, 32 rows}; rows beyond M are clipped by the tensor map
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && n_ok) {
-            const int row0 = m_blk * kBlockM + quarter * 32;
+          const int row0 = m_blk * kBlockM + quarter * 32;
+          if (lane == 0 && n_ok && row0 < p.M) {
             if constexpr (kEpi == EPI_RESID_F32) ptx::tma_reduce_add_2d(&tmap_out, stg, n, row0);
             else ptx::tma_store_2d(&tmap_out, stg, n, row0);
             ptx::bulk_commit_group();
@@ -383,7 +414,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if constexpr (kCta == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's MMA warp waits for both CTAs
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if constexpr (kTmaOut) {
@@ -392,10 +426,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) ptx::cluster_sync_all();  // no CTA may exit while its pair still signals / reads it
+  else __syncthreads();
   if (warp_idx == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, 2 * kAccumStride);
+    ptx::tmem_dealloc<kCta>(tmem_base, 2 * kAccumStride);
   }
 }
 

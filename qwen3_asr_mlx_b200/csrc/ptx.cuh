@@ -135,30 +135,36 @@ __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// cta_group::2 flavours: data lands in this CTA's smem, complete_tx is signalled on the
-// barrier at offset `bar` of the *leader* CTA (bit 24 of the cluster-shared address cleared).
-__device__ __forceinline__ uint32_t leader_bar_addr(uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
-__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1) {
+// shared::cluster address of the variable at local shared address `addr` in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+// cta_group::2 flavours: data lands in THIS CTA's smem, complete_tx is signalled on the mbarrier
+// whose shared::cluster address is `bar_cluster_addr` (the leader CTA's barrier of the pair).
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* t, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
       "%4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(t)), "r"(leader_bar_addr(bar)), "r"(c0), "r"(c1)
+      "l"(reinterpret_cast<uint64_t>(t)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1,
-                                                int c2) {
+__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* t, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
       "%4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(t)), "r"(leader_bar_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "l"(reinterpret_cast<uint64_t>(t)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1,
-                                                int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* t, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
       "%4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(t)), "r"(leader_bar_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "l"(reinterpret_cast<uint64_t>(t)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/qasr.h"
+#include "attention_sm100.cuh"
 #include "encoder_kernels.cuh"
 #include "gemm_host.cuh"
 #include "mel.cuh"
@@ -28,6 +29,7 @@ constexpr int kTokensPerChunk = 13;   // f^3(100)
 constexpr int kStemC = 480;
 constexpr int kStemGroupDefault = 1024;
 constexpr int kGemmStages = 4;
+constexpr int kPairStages = 6;  // CTA-pair kernels stage half of B per CTA: 32 KB / stage
 
 inline uint16_t f32_to_bf16(float f) {
   uint32_t u;
@@ -52,11 +54,17 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// Weight tensor maps for the single-CTA kernel (box = BLOCK_N rows) and for the CTA-pair kernel
+// (each CTA loads half of the B rows: box = BLOCK_N / 2 rows).
+struct WeightMaps {
+  CUtensorMap m1, m2;
+};
+
 struct LayerWeights {
   __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
-  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+  WeightMaps tm_wqkv, tm_wo, tm_w1, tm_w2;
 };
 
 }  // namespace
@@ -68,6 +76,8 @@ struct qasr_handle {
   bool finalized = false;
   bool debug = false;
   bool conv1_fp32 = false;  // QASR_CONV1_FP32=1 selects the CUDA-core fp32-weight conv1 (A/B testing)
+  bool attn_tc = true;      // QASR_ATTN_TC=0 selects the mma.sync attention kernel instead of the tcgen05 one
+  bool cta_pair = true;     // QASR_CTA_PAIR=0 selects the single-CTA (cta_group::1) GEMM kernels
   qasr_stats stats{};
 
   std::map<std::string, std::vector<float>> staged;  // host copies until finalize
@@ -85,7 +95,7 @@ struct qasr_handle {
   float *conv1_w = nullptr, *conv1_b = nullptr, *conv2_b = nullptr, *conv3_b = nullptr;
   __nv_bfloat16 *conv2_w = nullptr, *conv3_w = nullptr, *convout_w = nullptr, *proj1_w = nullptr, *proj2_w = nullptr;
   float *proj1_b = nullptr, *proj2_b = nullptr, *lnp_g = nullptr, *lnp_b = nullptr, *pe = nullptr;
-  CUtensorMap tm_conv2_w, tm_conv3_w, tm_convout_w, tm_proj1_w, tm_proj2_w;
+  WeightMaps tm_conv2_w, tm_conv3_w, tm_convout_w, tm_proj1_w, tm_proj2_w;
   std::vector<LayerWeights> layers;
 
   // workspace (grow-only)
@@ -96,7 +106,7 @@ struct qasr_handle {
   DevBuf d_chunks, d_rowmap, d_windows, d_soffs, d_foffs, d_boffs, d_uttmax;
   DevBuf dbg_stem, dbg_layer0, dbg_hidden;
   long long dbg_tokens = 0;
-  CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1;
+  CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1, tm_qkv;
   // per-category CUDA-event profiling (qasr_set_profile)
   bool profile = false;
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
@@ -242,6 +252,7 @@ int init_mel_tables(qasr_handle* h) {
   if ((rc = upload<float>(h, &h->d_fb_weight, wts))) return rc;
   QCUDA(h, cudaFuncSetAttribute(mel_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(MelSmem))));
+  QCUDA(h, cudaFuncSetAttribute(window_attention_sm100, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
   return QASR_OK;
 }
 
@@ -294,17 +305,19 @@ int build_weight_maps(qasr_handle* h) {
   const qasr_config& c = h->cfg;
   std::string e;
   const int D = c.d_model, F = c.encoder_ffn_dim;
-  if (!make_tmap_conv_w(&h->tm_conv2_w, h->conv2_w, kStemC, kStemC, 240, &e)) return fail(h, QASR_ERR_CUDA, e);
-  if (!make_tmap_conv_w(&h->tm_conv3_w, h->conv3_w, kStemC, kStemC, 240, &e)) return fail(h, QASR_ERR_CUDA, e);
-  if (!make_tmap_rows(&h->tm_convout_w, h->convout_w, D, 16 * kStemC, 16 * kStemC, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-  if (!make_tmap_rows(&h->tm_proj1_w, h->proj1_w, D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-  if (!make_tmap_rows(&h->tm_proj2_w, h->proj2_w, c.output_dim, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-  for (auto& L : h->layers) {
-    if (!make_tmap_rows(&L.tm_wqkv, L.wqkv, 3 * D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&L.tm_wo, L.wo, D, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&L.tm_w1, L.w1, F, D, D, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&L.tm_w2, L.w2, D, F, F, 256, &e)) return fail(h, QASR_ERR_CUDA, e);
-  }
+  auto rows = [&](WeightMaps& m, const void* w, uint64_t n, uint64_t k) {
+    return make_tmap_rows(&m.m1, w, n, k, k, 256, &e) && make_tmap_rows(&m.m2, w, n, k, k, 128, &e);
+  };
+  auto conv = [&](WeightMaps& m, const void* w) {
+    return make_tmap_conv_w(&m.m1, w, kStemC, kStemC, 240, &e) && make_tmap_conv_w(&m.m2, w, kStemC, kStemC, 120, &e);
+  };
+  bool ok = conv(h->tm_conv2_w, h->conv2_w) && conv(h->tm_conv3_w, h->conv3_w) &&
+            rows(h->tm_convout_w, h->convout_w, D, 16 * kStemC) && rows(h->tm_proj1_w, h->proj1_w, D, D) &&
+            rows(h->tm_proj2_w, h->proj2_w, c.output_dim, D);
+  for (auto& L : h->layers)
+    ok = ok && rows(L.tm_wqkv, L.wqkv, 3 * D, D) && rows(L.tm_wo, L.wo, D, D) && rows(L.tm_w1, L.w1, F, D) &&
+         rows(L.tm_w2, L.w2, D, F);
+  if (!ok) return fail(h, QASR_ERR_CUDA, e);
   return QASR_OK;
 }
 
@@ -334,13 +347,14 @@ int ensure_workspace(qasr_handle* h, long long tokens, long long chunks, long lo
     const int wide = F > D ? F : D;
     if ((rc = dev_alloc(h, h->x, static_cast<size_t>(n) * D * 4, false))) return rc;
     if ((rc = dev_alloc(h, h->xn, static_cast<size_t>(n) * D * 2, true))) return rc;
-    if ((rc = dev_alloc(h, h->qkv, static_cast<size_t>(n) * 3 * D * 2, false))) return rc;
+    if ((rc = dev_alloc(h, h->qkv, static_cast<size_t>(n) * 3 * D * 2, true))) return rc;  // zeroed: attention tiles over-read finite rows
     if ((rc = dev_alloc(h, h->attn, static_cast<size_t>(n) * D * 2, true))) return rc;
     if ((rc = dev_alloc(h, h->hbuf, static_cast<size_t>(n) * wide * 2, true))) return rc;
     if (!make_tmap_rows(&h->tm_xn, h->xn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
     if (!make_tmap_rows(&h->tm_attn, h->attn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
     if (!make_tmap_rows(&h->tm_h, h->hbuf.p, n, F, F, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
     if (!make_tmap_rows(&h->tm_p1, h->hbuf.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&h->tm_qkv, h->qkv.p, n, 3 * D, 3 * D, 128, &e)) return fail(h, QASR_ERR_CUDA, e);
     h->cap_tokens = n;
   }
   if (chunks > h->cap_chunks) {
@@ -429,7 +443,7 @@ int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __
 }
 
 template <int EPI>
-int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, void* out,
+int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, int M, int N, int K, void* out,
           long long ldo, const float* bias, cudaStream_t st) {
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
   CUtensorMap tout;
@@ -440,7 +454,8 @@ int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const CUtensorMap& tw,
     toutp = &tout;
   }
   ProfScope ps(h, cat, st, 2.0 * M * N * K, 0.0);
-  QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI>(ta, tw, p, st, toutp)));
+  if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI, 2>(ta, tw.m2, p, st, toutp)));
+  else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI, 1>(ta, tw.m1, p, st, toutp)));
   return QASR_OK;
 }
 
@@ -582,7 +597,8 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.out = h->planes2.p; p.bias = h->conv2_b;
       p.out_Hp = 17; p.out_Wp = 14; p.out_plane_stride = ps2; p.out_C = kStemC;
       ProfScope ps(h, QASR_PROF_CONV2, st, 2.0 * 32 * 25 * kStemC * 9 * kStemC * g, 0.0);
-      QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES>(h->tm_planes1, h->tm_conv2_w, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_PLANES, 2>(h->tm_planes1, h->tm_conv2_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES, 1>(h->tm_planes1, h->tm_conv2_w.m1, p, st)));
     }
     {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
       GemmParams p{};
@@ -593,14 +609,16 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
       p.out = h->flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
       ProfScope ps(h, QASR_PROF_CONV3, st, 2.0 * 16 * 13 * kStemC * 9 * kStemC * g, 0.0);
-      QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT>(h->tm_planes2, h->tm_conv3_w, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_FLAT, 2>(h->tm_planes2, h->tm_conv3_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT, 1>(h->tm_planes2, h->tm_conv3_w.m1, p, st)));
     }
     {  // conv_out + positional embedding + strip padding + pack (encoder.py:277-293)
       GemmParams p = dense_params(g * kTokensPerChunk, D, 16 * kStemC, x, D, nullptr);
       p.row_map = static_cast<const int*>(h->d_rowmap.p) + c0 * kTokensPerChunk;
       p.pe = h->pe; p.pe_period = kTokensPerChunk;
       ProfScope ps(h, QASR_PROF_CONV_OUT, st, 2.0 * g * kTokensPerChunk * D * 16 * kStemC, 0.0);
-      QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK>(h->tm_flat3, h->tm_convout_w, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_CONVOUT_PACK, 2>(h->tm_flat3, h->tm_convout_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK, 1>(h->tm_flat3, h->tm_convout_w.m1, p, st)));
     }
   }
   if (h->debug) {
@@ -622,8 +640,15 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
     if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, h->tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
     {
       ProfScope ps(h, QASR_PROF_ATTENTION, st, attn_flops, 8.0 * n * D);
-      window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
-          qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+      if (h->attn_tc) {
+        const long long items = nwin * H;
+        const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
+        window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(h->tm_qkv, static_cast<const WindowDesc*>(h->d_windows.p),
+                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e);
+      } else {
+        window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
+            qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+      }
     }
     QCUDA(h, cudaGetLastError());
     if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, h->tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
@@ -684,6 +709,8 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   if (rc) { g_last_error = h->err; delete h; return rc; }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaSetDevice failed"); }
   if (const char* c1 = getenv("QASR_CONV1_FP32")) h->conv1_fp32 = atoi(c1) != 0;
+  if (const char* cp = getenv("QASR_CTA_PAIR")) h->cta_pair = atoi(cp) != 0;
+  if (const char* at = getenv("QASR_ATTN_TC")) h->attn_tc = atoi(at) != 0;
   if (const char* sg = getenv("QASR_STEM_GROUP")) {
     const int v = atoi(sg);
     if (v > 0) h->stem_group = v;
@@ -1172,7 +1199,7 @@ int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float
   QCUDA(h, cudaMalloc(&da, static_cast<size_t>(M) * K * 2));
   QCUDA(h, cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
   QCUDA(h, cudaMalloc(&dout, static_cast<size_t>(M) * N * 4));
-  if (mode == 2) QCUDA(h, cudaMemcpy(dout, out, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
+  if ((mode & 15) == 2) QCUDA(h, cudaMemcpy(dout, out, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
   QCUDA(h, cudaMemcpy(da, a, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
   QCUDA(h, cudaMemcpy(dw, w, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
   if (bias) {
@@ -1181,12 +1208,18 @@ int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float
   }
   CUtensorMap ta, tw;
   std::string e;
-  if (!make_tmap_rows(&ta, da, M, K, K, kBlockM, &e) || !make_tmap_rows(&tw, dw, N, K, K, 256, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
+  const bool pair = (mode & 16) != 0;
+  mode &= 15;
+  if (!make_tmap_rows(&ta, da, M, K, K, kBlockM, &e) || !make_tmap_rows(&tw, dw, N, K, K, pair ? 128 : 256, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
   GemmParams p = dense_params(M, N, K, dout, N, static_cast<const float*>(db));
   CUtensorMap tout;
   if (!make_tmap_out_f32(&tout, dout, M, N, N, &e)) return fail(nullptr, QASR_ERR_CUDA, e);
-  if (mode == 1) QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_GELU_F32>(ta, tw, p, 0)));
-  else if (mode == 2) {  // residual mode: out is pre-filled by the caller (bias vector replicated) and accumulated into
+  if (pair) {
+    if (mode == 1) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_GELU_F32, 2>(ta, tw, p, 0)));
+    else if (mode == 2) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_RESID_F32, 2>(ta, tw, p, 0, &tout)));
+    else QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_STORE_F32, 2>(ta, tw, p, 0, &tout)));
+  } else if (mode == 1) QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_GELU_F32>(ta, tw, p, 0)));
+  else if (mode == 2) {  // residual mode: out is pre-filled by the caller and accumulated into
     QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_RESID_F32>(ta, tw, p, 0, &tout)));
   } else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_STORE_F32>(ta, tw, p, 0, &tout)));
   QCUDA(h, cudaDeviceSynchronize());

@@ -29,6 +29,35 @@ def to_bf16_bits(a: np.ndarray) -> np.ndarray:
     return (bf16_round(a).view(np.uint32) >> 16).astype(np.uint16)
 
 
+def stage_gemm_pair():
+    """cta_group::2 kernel (mode + 16): store / gelu / residual epilogues."""
+    from qwen3_asr_mlx_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(256, 256, 64), (128, 256, 128), (300, 1024, 1024), (1000, 3072, 1024), (2000, 1024, 4096), (13, 256, 7680)]:
+        a = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+        w = bf16_round((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32))
+        bias = rng.standard_normal(N).astype(np.float32)
+        ab, wb = to_bf16_bits(a), to_bf16_bits(w)
+        ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
+        for mode in (16, 18):
+            out = rng.standard_normal((M, N)).astype(np.float32) if mode == 18 else np.zeros((M, N), dtype=np.float32)
+            base = out.copy()
+            rc = lib.qasr_test_gemm(0, ab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), wb.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)),
+                                    bias.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), M, N, K, mode,
+                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+            if rc != 0:
+                print(f"gemm_pair {M}x{N}x{K} mode {mode}: rc={rc} {_lib.last_error()}")
+                continue
+            want = ref + base if mode == 18 else ref
+            err = np.abs(out - want).max()
+            print(f"gemm_pair {M}x{N}x{K} mode {mode}: max_abs_err={err:.3e} {'OK' if err < 2e-3 else 'FAIL'}")
+            if err >= 2e-3:
+                bad = np.argwhere(np.abs(out - want) > 2e-3)
+                print("   rows bad:", np.unique(bad[:, 0])[:12].tolist(), "cols bad:", np.unique(bad[:, 1])[:12].tolist(), "n_bad", len(bad))
+
+
 def stage_gemm():
     from qwen3_asr_mlx_b200 import _lib
 
@@ -186,7 +215,7 @@ def stage_enc_full():
     print("stats", enc.stats())
 
 
-STAGES = {"gemm": stage_gemm, "mel": stage_mel, "enc_small": stage_enc_small, "enc_full": stage_enc_full}
+STAGES = {"gemm": stage_gemm, "gemm_pair": stage_gemm_pair, "mel": stage_mel, "enc_small": stage_enc_small, "enc_full": stage_enc_full}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--stage":

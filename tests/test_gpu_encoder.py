@@ -43,8 +43,9 @@ def full():
     enc.close()
 
 
+@pytest.mark.parametrize("pair", [0, 16], ids=["cta_group1", "cta_group2"])
 @pytest.mark.parametrize("shape", [(128, 256, 64), (1, 256, 64), (300, 1024, 1024), (130, 2048, 4096), (1000, 3072, 1024)])
-def test_tcgen05_gemm_kernel(shape):
+def test_tcgen05_gemm_kernel(shape, pair):
     from qwen3_asr_mlx_b200 import _lib
 
     M, N, K = shape
@@ -56,13 +57,13 @@ def test_tcgen05_gemm_kernel(shape):
     lib = _lib.load()
     u16, f32 = ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_float)
     ab, wb = bf16_bits(a), bf16_bits(w)
-    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 0, out.ctypes.data_as(f32)))
+    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 0 + pair, out.ctypes.data_as(f32)))
     ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
     assert np.abs(out - ref).max() <= 1e-4  # fp32 accumulation of exact bf16 products
     # residual epilogue (TMA reduce-add into an fp32 matrix that already holds values)
     resid = rng.standard_normal((M, N)).astype(np.float32)
     acc = resid.copy()
-    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 2, acc.ctypes.data_as(f32)))
+    _lib.check(lib.qasr_test_gemm(0, ab.ctypes.data_as(u16), wb.ctypes.data_as(u16), bias.ctypes.data_as(f32), M, N, K, 2 + pair, acc.ctypes.data_as(f32)))
     assert np.abs(acc - (ref + resid)).max() <= 1e-4
 
 
@@ -146,6 +147,52 @@ def test_stem_grouping_is_transparent(small, monkeypatch):
     enc2.load_weights(params)
     assert np.array_equal(np.array(enc2(mel)), ref)
     enc2.close()
+
+
+@pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_GRAPHS": "0"}],
+                         ids=["single_cta_gemm", "mma_sync_attention", "all_fallback_kernels_eager"])
+def test_kernel_variants_agree(small, monkeypatch, env):
+    """The alternative kernels (cta_group::1 GEMM, mma.sync attention, eager launches) give the same
+    embeddings as the default configuration (cta_group::2 GEMM, tcgen05 attention, graph replay)."""
+    from qwen3_asr_mlx_b200 import AudioEncoder
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(21)
+    mels = [mel_np.log_mel_spectrogram_fast(synth(rng, int(n))) for n in (16000 * 11 + 999, 30000, 16000 * 30)]
+    ref, _ = enc.encode_batch(mels)
+    ref = np.array(ref)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = AudioEncoder(cfg)
+    alt.load_weights(params)
+    for _ in range(3):  # eager, captured, replayed
+        got = np.array(alt.encode_batch(mels)[0])
+        assert rel_err(got, ref) <= 2e-3
+    for u, m in enumerate(mels):
+        assert rel_err(np.array(alt(m))[0], encoder_torch.encoder_forward(params, cfg, m)) <= EMB_TOL
+    alt.close()
+
+
+def test_graph_replay_matches_eager(small):
+    """Same buffers three times: eager, graph capture, graph replay -> identical embeddings."""
+    import torch
+
+    cfg, params, enc = small
+    x = synth(np.random.default_rng(33), 16000 * 17 + 77)
+    audio = torch.from_numpy(x).cuda()
+    soffs = np.array([0, len(x)], dtype=np.int64)
+    out = torch.empty((enc.num_tokens(len(x) // 160), cfg.output_dim), dtype=torch.float32, device="cuda")
+    results = []
+    for _ in range(4):
+        out.zero_()
+        enc.encode_packed_audio(audio, soffs, out=out)
+        results.append(out.cpu().numpy().copy())
+    assert all(np.array_equal(results[0], r) for r in results[1:])
+    audio.copy_(torch.from_numpy(synth(np.random.default_rng(34), len(x))).cuda())  # new content, same buffers: replayed graph must see it
+    enc.encode_packed_audio(audio, soffs, out=out)
+    assert not np.array_equal(out.cpu().numpy(), results[0])
+    fresh = np.array(enc.encode_audio_batch([audio.cpu().numpy()])[0])
+    assert np.array_equal(out.cpu().numpy(), fresh)
 
 
 def test_full_arch_config1_parity(full):
