@@ -61,6 +61,24 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "encoder_small.npz"), audio=x, emb=emb.astype(np.float32),
                         cfg=np.array([cfg.d_model, cfg.encoder_layers, cfg.encoder_attention_heads, cfg.encoder_ffn_dim, cfg.output_dim]),
                         seed=np.array(7))
+    # _find_split_points (model.py:454-513) executed verbatim: the function is pure numpy, but its module imports
+    # mlx at top level, so the def is extracted with ast and exec'd alone.
+    import ast
+    src = open("/root/reference/src/qwen3_asr_mlx/model.py").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "_find_split_points")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "reference_model_py", "exec"), ns)
+    ref_split = ns["_find_split_points"]
+    cases = {}
+    # inputs are regenerated from the seed by the test (numpy's PCG64 stream is stable), only the answers are stored
+    for i, (name, (n, chunk, search)) in enumerate({"a": (16000 * 25, 160000, 80000), "b": (16000 * 61 + 123, 480000, 80000),
+                                                   "c": (16000 * 7, 16000, 32000), "d": (16000 * 33, 160000, 16000),
+                                                   "e": (5000, 1000, 480)}.items()):
+        r = np.random.default_rng(4200 + i)
+        x = (r.standard_normal(n) * np.abs(np.sin(np.arange(n) / 9000.0))).astype(np.float32)
+        cases[name + "_args"] = np.array([n, chunk, search, 4200 + i])
+        cases[name + "_points"] = np.array(ref_split(x, chunk, search), dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "split_points_reference.npz"), **cases)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

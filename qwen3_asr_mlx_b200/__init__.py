@@ -11,6 +11,7 @@ from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
 from .config import AudioEncoderConfig
 from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
 from ._array import DeviceArray
+from .model import LANGUAGE_MAP, Qwen3ASR, TranscriptionResult
 
 __all__ = [
     "__version__",
@@ -22,4 +23,7 @@ __all__ = [
     "SinusoidalPositionEmbedding",
     "load_encoder_weights",
     "DeviceArray",
+    "Qwen3ASR",
+    "TranscriptionResult",
+    "LANGUAGE_MAP",
 ]
