@@ -7,9 +7,14 @@
 //   warp 1        MMA issuer:   S = Q K^T   SS mode, M=128 N=112 K=64  -> TMEM slot j&1, columns [0,112)
 //                               O = P V     TS mode (P read from TMEM), V is the MN-major B operand,
 //                                           M=128 N=64 K=16*ceil(len/16) -> columns [192,256)
-//   warps 2-5     softmax + epilogue, one thread per query row: tcgen05.ld S -> fp32 softmax in
-//                 registers -> bf16 P via tcgen05.st into columns [128,184) -> ... -> tcgen05.ld O,
-//                 scale by 1/sum, bf16, swizzled-smem transpose, 16-byte coalesced stores
+//   warps 2-5     softmax + epilogue group 0 (even items, TMEM slot 0), one thread per query row:
+//   warps 6-9     softmax + epilogue group 1 (odd items,  TMEM slot 1)
+//                 tcgen05.ld S -> fp32 softmax in registers -> bf16 P via tcgen05.st into columns
+//                 [128,184) -> ... -> tcgen05.ld O, scale by 1/sum, bf16, swizzled-smem transpose,
+//                 16-byte coalesced stores.  Two groups keep two warps per scheduler busy (the
+//                 single-group version was bound by instruction latency: ncu 4.3 cycles / issue).
+// The MMA thread polls (try_wait) its two kinds of pending work, S = QK^T of the next item and
+// O = PV of the oldest item, so neither can block the other.
 // The O(n^2) additive mask of the reference never exists: keys beyond the window length get
 // probability exactly 0.  Rows / keys of the 128-token tiles that lie beyond the window are
 // finite values of neighbouring tokens (or TMA zero fill) and never reach a stored output.
@@ -19,10 +24,10 @@
 
 namespace qasr {
 
-constexpr int kAtThreads = 192;
+constexpr int kAtThreads = 320;
 constexpr int kAtTileBytes = 128 * 128;            // 128 tokens x 64 bf16
 constexpr int kAtStageBytes = 3 * kAtTileBytes;    // Q, K, V
-constexpr int kAtStagingBytes = 4 * 32 * 128;      // per softmax warp: 32 rows x 128 B
+constexpr int kAtStagingBytes = 8 * 32 * 128;      // per softmax warp: 32 rows x 128 B
 constexpr int kAtStages = 4;
 constexpr int kAtSmemBytes = kAtStages * kAtStageBytes + kAtStagingBytes + 256 + 1024;
 constexpr int kAtKeysPadded = 112;                 // 104 rounded up to a multiple of 16
@@ -93,50 +98,56 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
     if (lane == 0) {
       constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, kAtKeysPadded);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-      auto issue_qk = [&](int j) {
-        const int st = j % kAtStages, slot = j & 1;
-        ptx::mbar_wait(&full[st], (j / kAtStages) & 1);
-        ptx::mbar_wait(&tfree[slot], ((j >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint8_t* sb = stage_base + st * kAtStageBytes;
-        const uint64_t qd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sb));
-        const uint64_t kd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sb + kAtTileBytes));
-        const uint32_t tmem_s = tmem_base + slot * kAtSlotCols;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_bf16_ss<1>(tmem_s, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-        ptx::umma_commit(&s_full[slot]);
-      };
       int n_mine = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) ++n_mine;
-      if (n_mine > 0) issue_qk(0);
-      int j = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++j) {
-        if (j + 1 < n_mine) issue_qk(j + 1);  // overlaps the softmax of item j
-        const int st = j % kAtStages, slot = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int len = windows[item / num_heads].len;
-        const int ksteps = (len + 15) >> 4;
-        ptx::mbar_wait(&p_ready[slot], ph);
-        ptx::tc_fence_after();
-        const uint8_t* sb = stage_base + st * kAtStageBytes;
-        // V tile: 64 dims (one 128-byte swizzle row) per key, 8-key groups 1024 B apart
-        const uint64_t vd = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sb + 2 * kAtTileBytes), 1024, 1024);
-        const uint32_t tmem_p = tmem_base + slot * kAtSlotCols + kAtPCol;
-        const uint32_t tmem_o = tmem_base + slot * kAtSlotCols + kAtOCol;
-        for (int k = 0; k < ksteps; ++k)  // 16 keys per step: 8 packed TMEM columns of P, 2048 B of V
-          ptx::umma_bf16_ts(tmem_o, tmem_p + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc_pv, k != 0);
-        ptx::umma_commit(&o_full[slot]);
-        ptx::umma_commit(&sempty[st]);
+      int next_qk = 0, next_pv = 0;
+      while (next_pv < n_mine) {
+        // S = Q K^T of item next_qk: needs its smem stage and a drained TMEM slot (at most 2 items ahead of PV)
+        if (next_qk < n_mine && next_qk < next_pv + 2) {
+          const int j = next_qk, st = j % kAtStages, slot = j & 1;
+          if (ptx::mbar_try_wait(&full[st], (j / kAtStages) & 1) && ptx::mbar_try_wait(&tfree[slot], ((j >> 1) & 1) ^ 1)) {
+            ptx::tc_fence_after();
+            const uint8_t* sb = stage_base + st * kAtStageBytes;
+            const uint64_t qd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sb));
+            const uint64_t kd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sb + kAtTileBytes));
+            const uint32_t tmem_s = tmem_base + slot * kAtSlotCols;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_bf16_ss<1>(tmem_s, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+            ptx::umma_commit(&s_full[slot]);
+            ++next_qk;
+            continue;
+          }
+        }
+        // O = P V of item next_pv: needs the probabilities written by its softmax group
+        if (next_pv < next_qk) {
+          const int j = next_pv, st = j % kAtStages, slot = j & 1;
+          if (ptx::mbar_try_wait(&p_ready[slot], (j >> 1) & 1)) {
+            ptx::tc_fence_after();
+            const int item = blockIdx.x + j * gridDim.x;
+            const int len = windows[item / num_heads].len;
+            const int ksteps = (len + 15) >> 4;
+            const uint8_t* sb = stage_base + st * kAtStageBytes;
+            // V tile: 64 dims (one 128-byte swizzle row) per key, 8-key groups 1024 B apart
+            const uint64_t vd = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sb + 2 * kAtTileBytes), 1024, 1024);
+            const uint32_t tmem_p = tmem_base + slot * kAtSlotCols + kAtPCol;
+            const uint32_t tmem_o = tmem_base + slot * kAtSlotCols + kAtOCol;
+            for (int k = 0; k < ksteps; ++k)  // 16 keys per step: 8 packed TMEM columns of P, 2048 B of V
+              ptx::umma_bf16_ts(tmem_o, tmem_p + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc_pv, k != 0);
+            ptx::umma_commit(&o_full[slot]);
+            ptx::umma_commit(&sempty[st]);
+            ++next_pv;
+          }
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue (warps 2..5)
     const int quarter = warp_idx & 3;            // TMEM lane quarter accessible to this warp
-    const int row = quarter * 32 + lane;         // query row of this thread
+    const int group = (warp_idx - 2) >> 2;       // 0: even items / slot 0, 1: odd items / slot 1
     uint4* stg = reinterpret_cast<uint4*>(staging) + (warp_idx - 2) * (32 * 8);
-    int j = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++j) {
-      const int st = j & 1;
+    for (int j = group; blockIdx.x + static_cast<long long>(j) * gridDim.x < num_items; j += 2) {
+      const int item = blockIdx.x + j * gridDim.x;
+      const int st = group;                      // TMEM slot
       const uint32_t ph = (j >> 1) & 1;
       const WindowDesc wd = windows[item / num_heads];
       const int head = item % num_heads;
@@ -152,30 +163,40 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
       ptx::tmem_ld_32x32(tmem_s + 64, s2);
       ptx::tmem_ld_32x16(tmem_s + 96, s3);
       ptx::tmem_ld_wait();
-      float mx = -INFINITY;
+      // Columns >= len are masked.  `len` is uniform, so fully valid 32-column blocks take a mask-free path.
+      auto block_max = [&](uint32_t (&s)[32], int c0) {
+        float m = -INFINITY;
+        if (len >= c0 + 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i >= len) s0[i] = 0xff800000u;
-        if (32 + i >= len) s1[i] = 0xff800000u;
-        if (64 + i >= len) s2[i] = 0xff800000u;
-        mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), fmaxf(__uint_as_float(s1[i]), __uint_as_float(s2[i]))));
-      }
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(s[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c0 + i >= len) s[i] = 0xff800000u;  // -inf -> probability exactly 0
+            m = fmaxf(m, __uint_as_float(s[i]));
+          }
+        }
+        return m;
+      };
+      float mx = fmaxf(fmaxf(block_max(s0, 0), block_max(s1, 32)), block_max(s2, 64));
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (96 + i >= len) s3[i] = 0xff800000u;
         mx = fmaxf(mx, __uint_as_float(s3[i]));
       }
       const float moff = mx * scale_log2e;
+      auto ex2 = [&](uint32_t sv) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(__uint_as_float(sv), scale_log2e, -moff)));
+        return r;
+      };
       float sum = 0.0f;
       uint32_t p0[16], p1[16], p2[16], p3[8];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a0 = exp2f(fmaf(__uint_as_float(s0[2 * i]), scale_log2e, -moff));
-        const float a1 = exp2f(fmaf(__uint_as_float(s0[2 * i + 1]), scale_log2e, -moff));
-        const float b0 = exp2f(fmaf(__uint_as_float(s1[2 * i]), scale_log2e, -moff));
-        const float b1 = exp2f(fmaf(__uint_as_float(s1[2 * i + 1]), scale_log2e, -moff));
-        const float c0 = exp2f(fmaf(__uint_as_float(s2[2 * i]), scale_log2e, -moff));
-        const float c1 = exp2f(fmaf(__uint_as_float(s2[2 * i + 1]), scale_log2e, -moff));
+        const float a0 = ex2(s0[2 * i]), a1 = ex2(s0[2 * i + 1]);
+        const float b0 = ex2(s1[2 * i]), b1 = ex2(s1[2 * i + 1]);
+        const float c0 = ex2(s2[2 * i]), c1 = ex2(s2[2 * i + 1]);
         sum += (a0 + a1) + (b0 + b1) + (c0 + c1);
         p0[i] = ptx::pack_bf16x2(a0, a1);
         p1[i] = ptx::pack_bf16x2(b0, b1);
@@ -183,8 +204,7 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float a0 = exp2f(fmaf(__uint_as_float(s3[2 * i]), scale_log2e, -moff));
-        const float a1 = exp2f(fmaf(__uint_as_float(s3[2 * i + 1]), scale_log2e, -moff));
+        const float a0 = ex2(s3[2 * i]), a1 = ex2(s3[2 * i + 1]);
         sum += a0 + a1;
         p3[i] = ptx::pack_bf16x2(a0, a1);
       }
