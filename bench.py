@@ -249,21 +249,41 @@ def main():
     value = audio_s_per_step / (ms_per_step / 1e3)
 
     # ---------------------------------------------------------------- end to end through the C ABI with host buffers (`e2e`)
-    out_np = out_pinned.numpy()
-    audio_np = audio_pinned.numpy()
-    for _ in range(2):
-        enc.encode_audio_host(audio_np, soffs, out_np)
+    # Two pipeline slots, each with its own pinned host input and output: every step copies its 123 MB of audio
+    # host->device and its 204 MB of embeddings device->host; the copies of step i overlap the kernels of step i+-1.
+    audio_np = [audio_pinned.numpy(), torch.from_numpy(audio_host).pin_memory().numpy()]
+    out_np = [out_pinned.numpy(), torch.empty((n_tok, cfg.output_dim), dtype=torch.float32).pin_memory().numpy()]
+    for s in (0, 1, 0, 1):
+        enc.host_wait(s)
+        enc.encode_audio_host_async(s, audio_np[s], soffs, out_np[s])
+    enc.host_wait(0)
+    enc.host_wait(1)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     checksum = 0.0
-    for _ in range(args.steps):
-        enc.encode_audio_host(audio_np, soffs, out_np)  # H2D audio + kernels + D2H embeddings, synchronous
-        checksum += float(out_np[0, 0])
-    e1.record()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        s = i & 1
+        enc.host_wait(s)                       # result of step i-2 is on the host
+        if i >= 2:
+            checksum += float(out_np[s][0, 0])  # device->host read of that step's result
+        enc.encode_audio_host_async(s, audio_np[s], soffs, out_np[s])
+    enc.host_wait(0)
+    enc.host_wait(1)
+    checksum += float(out_np[0][0, 0]) + float(out_np[1][0, 0])
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_ms = max_over_ranks(e2e_wall_ms) / args.steps
     e2e_value = audio_s_per_step / (e2e_ms / 1e3)
+    # serial variant for reference: one synchronous qasr_encode_audio_host call per step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    enc.encode_audio_host(audio_np[0], soffs, out_np[0])
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        enc.encode_audio_host(audio_np[0], soffs, out_np[0])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_serial_ms = e0.elapsed_time(e1) / args.steps
 
     if rank == 0:
         # ------------------------------------------------------------ roofline of the dominant kernel
@@ -302,9 +322,9 @@ def main():
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_reference_sample(1)  # warm-up (thread pools, page-in)
-            a, t, threads = cpu_reference_sample(4)
+            a, t, threads = cpu_reference_sample(40)
             cpu_baseline = {"value": a / t, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"4 x {UTT_SECONDS} s utterances of the same workload ({t:.1f} s of CPU work); numpy mel (1 thread, per-frame loop as in the reference) + torch fp32 encoder (all cores)"}
+                            "sample": f"40 x {UTT_SECONDS} s utterances of the same workload ({t:.1f} s of CPU work); numpy mel (1 thread, per-frame loop as in the reference) + torch fp32 encoder (all cores)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -312,8 +332,11 @@ def main():
             "config": {"workload": "configs[1]: batch 64 x 30 s utterances per GPU, mel+encoder bf16 (fp32 accumulate, fp32 mel), Qwen3-ASR-1.7B arch random-init seed 1234",
                        "utterances_per_gpu": UTTS_PER_GPU, "utterance_seconds": UTT_SECONDS, "tokens_per_gpu": n_tok, "parallelism": f"dp{world} (one process per GPU, no forward collective)",
                        "l2": "no flush: per-step working set (~5 GB of activations, 123 MB audio in, 204 MB embeddings out) exceeds the 126 MB L2"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(audio_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes),
-                    "api": "qasr_encode_audio_host (pinned host audio in, pinned host fp32 embeddings out)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(audio_np[0].nbytes), "d2h_bytes_per_step": int(out_np[0].nbytes),
+                    "api": "qasr_encode_audio_host_async + qasr_host_wait, 2 slots (pinned host audio in, pinned host fp32 embeddings out; copies overlap the other slot's kernels)",
+                    "timing": "host wall clock around K submitted+completed steps (the pipeline spans 3 streams), max over ranks",
+                    "serial_ms_per_step": e2e_serial_ms, "serial_value": audio_s_per_step / (e2e_serial_ms / 1e3),
+                    "serial_api": "qasr_encode_audio_host (one synchronous call per step)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -119,6 +119,13 @@ int qasr_encode_host(qasr_handle* h, const float* mel_host, const int64_t* frame
 int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
                            void* emb_host, int out_dtype, int64_t* token_offsets_out);
 
+/* Double-buffered host pipeline: slot 0/1 each own device staging buffers; the H2D copy, the kernels and the D2H copy
+ * of a submission run on three streams, so that the copies of one submission overlap the kernels of the other slot's.
+ * token_offsets_out is filled before the call returns; emb_host is valid after qasr_host_wait(slot). */
+int qasr_encode_audio_host_async(qasr_handle* h, int32_t slot, const float* audio_host, const int64_t* sample_offsets,
+                                 int32_t batch, void* emb_host, int out_dtype, int64_t* token_offsets_out);
+int qasr_host_wait(qasr_handle* h, int32_t slot);
+
 /* ---- constant tables, as the library builds them (for parity tests) ---- */
 int qasr_mel_filterbank(float* out_128x201);
 int qasr_hann_window(float* out_400);

@@ -134,6 +134,11 @@ struct qasr_handle {
   uint64_t use_clock = 0;
   cudaStream_t own_stream = nullptr;  // used when the caller passes the legacy NULL stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // double-buffered host pipeline (qasr_encode_audio_host_async): copies on their own streams
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  DevBuf slot_in[2], slot_out[2];
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
 };
 
 namespace {
@@ -719,10 +724,19 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(nullptr, QASR_ERR_CUDA, "stream / event creation failed");
   }
+  for (int s = 0; s < 2; ++s)
+    if (cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_comp[s], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return fail(nullptr, QASR_ERR_CUDA, "event creation failed");
+    }
   rc = init_mel_tables(h);
   if (rc) { g_last_error = h->err; qasr_destroy(h); return rc; }
   *out = h;
@@ -746,6 +760,15 @@ void qasr_destroy(qasr_handle* h) {
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  for (int s = 0; s < 2; ++s) {
+    dev_free(h, h->slot_in[s]);
+    dev_free(h, h->slot_out[s]);
+    if (h->ev_h2d[s]) cudaEventDestroy(h->ev_h2d[s]);
+    if (h->ev_comp[s]) cudaEventDestroy(h->ev_comp[s]);
+    if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
+  }
   delete h;
 }
 
@@ -1102,6 +1125,59 @@ int qasr_encode_audio_host(qasr_handle* h, const float* audio_host, const int64_
   const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
   return host_call(h, CALL_ENCODE_AUDIO, audio_host, static_cast<size_t>(ns) * 4, sample_offsets, batch, emb_host,
                    static_cast<size_t>(ntok) * h->cfg.output_dim * esz, out_dtype, token_offsets_out);
+}
+
+int qasr_encode_audio_host_async(qasr_handle* h, int32_t slot, const float* audio_host, const int64_t* sample_offsets,
+                                 int32_t batch, void* emb_host, int out_dtype, int64_t* token_offsets_out) {
+  if (!h || !audio_host || !sample_offsets || !emb_host || batch <= 0 || slot < 0 || slot > 1)
+    return fail(h, QASR_ERR_INVALID, "qasr_encode_audio_host_async: bad argument");
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  if (h->slot_busy[slot]) return fail(h, QASR_ERR_STATE, "slot still in flight: call qasr_host_wait(slot) first");
+  const long long ns = sample_offsets[batch];
+  long long ntok = 0;
+  for (int u = 0; u < batch; ++u) {
+    const long long n = sample_offsets[u + 1] - sample_offsets[u];
+    if (n < kMelHop) return fail(h, QASR_ERR_INVALID, "need >= 160 samples per utterance");
+    int64_t t = 0;
+    qasr_count_tokens(h, n / kMelHop, &t);
+    ntok += t;
+  }
+  const size_t in_bytes = static_cast<size_t>(ns) * 4;
+  const size_t out_bytes = static_cast<size_t>(ntok) * h->cfg.output_dim * (out_dtype == QASR_BF16 ? 2 : 4);
+  if (in_bytes > h->slot_in[slot].bytes || out_bytes > h->slot_out[slot].bytes) {
+    QCUDA(h, cudaDeviceSynchronize());  // growing a slot buffer: nothing may still be using the old one
+    if ((rc = dev_alloc(h, h->slot_in[slot], in_bytes, false))) return rc;
+    if ((rc = dev_alloc(h, h->slot_out[slot], out_bytes, false))) return rc;
+  }
+  // H2D of this step (waits until the previous compute on this slot has consumed the input buffer)
+  QCUDA(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_comp[slot], 0));
+  QCUDA(h, cudaMemcpyAsync(h->slot_in[slot].p, audio_host, in_bytes, cudaMemcpyHostToDevice, h->h2d_stream));
+  QCUDA(h, cudaEventRecord(h->ev_h2d[slot], h->h2d_stream));
+  // compute (waits for the input, and for the previous D2H out of this slot's output buffer)
+  QCUDA(h, cudaStreamWaitEvent(h->own_stream, h->ev_h2d[slot], 0));
+  QCUDA(h, cudaStreamWaitEvent(h->own_stream, h->ev_done[slot], 0));
+  CallArgs c{CALL_ENCODE_AUDIO, static_cast<const float*>(h->slot_in[slot].p), h->slot_out[slot].p, sample_offsets, batch, out_dtype,
+             token_offsets_out};
+  if ((rc = dispatch(h, c, h->own_stream))) return rc;
+  QCUDA(h, cudaEventRecord(h->ev_comp[slot], h->own_stream));
+  // D2H of the embeddings
+  QCUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[slot], 0));
+  QCUDA(h, cudaMemcpyAsync(emb_host, h->slot_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+  QCUDA(h, cudaEventRecord(h->ev_done[slot], h->d2h_stream));
+  h->slot_busy[slot] = true;
+  return QASR_OK;
+}
+
+int qasr_host_wait(qasr_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot > 1) return fail(h, QASR_ERR_INVALID, "qasr_host_wait: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  if (!h->slot_busy[slot]) return QASR_OK;
+  QCUDA(h, cudaEventSynchronize(h->ev_done[slot]));
+  h->slot_busy[slot] = false;
+  return QASR_OK;
 }
 
 int qasr_mel_filterbank(float* out) {

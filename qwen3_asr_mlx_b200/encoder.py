@@ -198,6 +198,20 @@ class AudioEncoder:
                                              ctypes.c_void_p(out.ctypes.data), cdt, runtime.i64_ptr(toffs)))
         return toffs
 
+    def encode_audio_host_async(self, slot: int, audio: np.ndarray, soffs: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """Submit one batch into pipeline slot 0/1 (``qasr_encode_audio_host_async``): its H2D / kernels /
+        D2H overlap the other slot's.  ``out`` is valid after ``host_wait(slot)``; returns token offsets."""
+        self._ensure_weights()
+        h = self._handle
+        toffs = np.zeros(len(soffs), dtype=np.int64)
+        cdt = _lib.QASR_F32 if out.dtype == np.float32 else _lib.QASR_BF16
+        h.check(h.lib.qasr_encode_audio_host_async(h.ptr, int(slot), ctypes.c_void_p(audio.ctypes.data), runtime.i64_ptr(soffs),
+                                                   len(soffs) - 1, ctypes.c_void_p(out.ctypes.data), cdt, runtime.i64_ptr(toffs)))
+        return toffs
+
+    def host_wait(self, slot: int) -> None:
+        self._handle.check(self._handle.lib.qasr_host_wait(self._handle.ptr, int(slot)))
+
     def __call__(self, mel) -> DeviceArray:
         """``(n_mels, T)`` or ``(batch, n_mels, T)`` log-mel -> ``(1, n_tokens, output_dim)``."""
         emb, _ = self.encode_batch([mel])

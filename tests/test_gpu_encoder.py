@@ -231,6 +231,38 @@ def test_full_arch_host_entry_point(full):
     assert list(toffs) == list(toffs2) and np.array_equal(out, np.array(dev))
 
 
+def test_async_host_pipeline_matches_synchronous_call(small):
+    """qasr_encode_audio_host_async / qasr_host_wait with both slots in flight give the synchronous results."""
+    import torch
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(12)
+    batches = []
+    for k in range(5):
+        xs = [synth(rng, int(n)) for n in rng.integers(8000, 90000, size=3)]
+        soffs = np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.int64)
+        batches.append((np.concatenate(xs), soffs))
+    refs = []
+    for audio, soffs in batches:
+        n_tok = sum(enc.num_tokens(int(soffs[u + 1] - soffs[u]) // 160) for u in range(3))
+        out = np.empty((n_tok, cfg.output_dim), dtype=np.float32)
+        enc.encode_audio_host(audio, soffs, out)
+        refs.append(out)
+    pinned_in = [torch.empty(300000, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    outs = [np.empty_like(r) for r in refs]
+    for i, (audio, soffs) in enumerate(batches):
+        s = i & 1
+        enc.host_wait(s)
+        pinned_in[s][: len(audio)] = audio
+        enc.encode_audio_host_async(s, pinned_in[s][: len(audio)], soffs, outs[i])
+    enc.host_wait(0)
+    enc.host_wait(1)
+    for got, ref in zip(outs, refs):
+        assert np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        enc.encode_audio_host_async(2, batches[0][0], batches[0][1], outs[0])
+
+
 def test_full_arch_config2_size_properties(full):
     """BASELINE config 2 size (64 x 30 s on one B200): shape, finiteness, batch == single, spot parity."""
     cfg, params, enc = full
