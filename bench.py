@@ -22,6 +22,11 @@ import sys
 import threading
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (set before numpy/torch load)
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -119,6 +124,7 @@ def cpu_reference_sample(n_utts: int, seed: int = 1):
     from oracle import encoder_torch, mel_np
     from qwen3_asr_mlx_b200 import AudioEncoderConfig, weights
 
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     cfg = AudioEncoderConfig()
     params = cpu_reference_sample.params
     if params is None:
@@ -159,10 +165,23 @@ def run_reference(args, rank: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """Print the ONE JSON line on the real stdout (fd 1 is pointed at stderr while the bench runs, so that
+    library banners such as NCCL's version line cannot end up in front of it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -343,7 +362,7 @@ def main():
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
