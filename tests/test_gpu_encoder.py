@@ -149,8 +149,9 @@ def test_stem_grouping_is_transparent(small, monkeypatch):
     enc2.close()
 
 
-@pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_GRAPHS": "0"}],
-                         ids=["single_cta_gemm", "mma_sync_attention", "all_fallback_kernels_eager"])
+@pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CONV_HALF_TAIL": "1"}, {"QASR_CONV1_FP32": "1"},
+                                 {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_CONV_HALF_TAIL": "1", "QASR_GRAPHS": "0"}],
+                         ids=["single_cta_gemm", "mma_sync_attention", "conv_half_tail_block", "conv1_cuda_cores_fp32_weights", "all_alternative_kernels_eager"])
 def test_kernel_variants_agree(small, monkeypatch, env):
     """The alternative kernels (cta_group::1 GEMM, mma.sync attention, eager launches) give the same
     embeddings as the default configuration (cta_group::2 GEMM, tcgen05 attention, graph replay)."""
@@ -167,7 +168,7 @@ def test_kernel_variants_agree(small, monkeypatch, env):
     alt.load_weights(params)
     for _ in range(3):  # eager, captured, replayed
         got = np.array(alt.encode_batch(mels)[0])
-        assert rel_err(got, ref) <= 2e-3
+        assert rel_err(got, ref) <= 5e-3  # variants differ by bf16 rounding order (conv1 fp32 vs bf16 weights is the largest)
     for u, m in enumerate(mels):
         assert rel_err(np.array(alt(m))[0], encoder_torch.encoder_forward(params, cfg, m)) <= EMB_TOL
     alt.close()
