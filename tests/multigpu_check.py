@@ -1,0 +1,52 @@
+"""Multi-GPU check of the data-parallel launcher over NCCL (run under torchrun on >= 2 GPUs; not a pytest file):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multigpu_check.py
+
+Every rank encodes its LPT share of a ragged batch, the final all-gather-v restores the original order, and
+rank 0 checks the gathered embeddings bit-for-bit against a single-GPU encode of the whole batch.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from qwen3_asr_mlx_b200 import AudioEncoder, AudioEncoderConfig, launcher, weights  # noqa: E402
+from tests.helpers import synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = AudioEncoderConfig(encoder_layers=2)
+    enc = AudioEncoder(cfg, device=local)
+    enc.load_weights(weights.random_init(cfg, seed=1234))
+    rng = np.random.default_rng(99)
+    lengths = [int(n) for n in rng.integers(8000, 300000, size=23)]
+    audios = [synth(np.random.default_rng(1000 + i), n) for i, n in enumerate(lengths)]
+
+    def encode_fn(idx):
+        emb, toffs = enc.encode_audio_batch([audios[i] for i in idx])
+        return emb.tensor, toffs
+
+    emb, offs, mine = launcher.encode_sharded(encode_fn, lengths, cfg.output_dim, rank, world, tokens_per_call=2048)
+    ok = True
+    if rank == 0:
+        ref, ref_offs = enc.encode_audio_batch(audios)
+        ok = bool(torch.equal(emb, ref.tensor)) and list(offs) == list(ref_offs)
+        print(f"world={world} shares={[len(p) for p in launcher.lpt_partition([launcher.tokens_for_samples(n) for n in lengths], world)]} "
+              f"tokens={int(offs[-1])} gathered==single-GPU: {ok}")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
