@@ -75,27 +75,23 @@ inline bool make_tmap_rows(CUtensorMap* out, const void* base, uint64_t rows, ui
   return make_tmap_bf16(out, base, 2, dims, str, box, err);
 }
 
-// Parity-plane activation tensor [4 planes][rows_total][Wp][C] bf16; box {64, OW, rows_per_tile, 1}
-// (half = true: {32, ...} with SWIZZLE_64B, for the 32-channel tail block of a tap).
+// Parity-plane activation tensor [4 planes][rows_total][Wp][C] bf16; box {64, OW, rows_per_tile, 1}.
 inline bool make_tmap_conv_act(CUtensorMap* out, const void* base, int C, int Wp, uint64_t rows_total, int OW,
-                               int rows_per_tile, std::string* err, bool half = false) {
+                               int rows_per_tile, std::string* err) {
   uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Wp), rows_total, 4};
   uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * Wp * 2,
                      static_cast<uint64_t>(C) * Wp * rows_total * 2};
-  uint32_t box[4] = {static_cast<uint32_t>(half ? kBlockK / 2 : kBlockK), static_cast<uint32_t>(OW),
+  uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(OW),
                      static_cast<uint32_t>(rows_per_tile), 1};
-  return make_tmap(out, base, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                   half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, err);
+  return make_tmap_bf16(out, base, 4, dims, str, box, err);
 }
 
 // Convolution weights [O][9 taps][C] bf16 (the reference's (O,kH,kW,I) layout flattened); box {64, 1, block_n}.
-inline bool make_tmap_conv_w(CUtensorMap* out, const void* base, int C, int O, uint32_t block_n, std::string* err,
-                             bool half = false) {
+inline bool make_tmap_conv_w(CUtensorMap* out, const void* base, int C, int O, uint32_t block_n, std::string* err) {
   uint64_t dims[3] = {static_cast<uint64_t>(C), 9, static_cast<uint64_t>(O)};
   uint64_t str[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 9 * 2};
-  uint32_t box[3] = {static_cast<uint32_t>(half ? kBlockK / 2 : kBlockK), 1, block_n};
-  return make_tmap(out, base, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                   half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, err);
+  uint32_t box[3] = {static_cast<uint32_t>(kBlockK), 1, block_n};
+  return make_tmap_bf16(out, base, 3, dims, str, box, err);
 }
 
 inline int gemm_num_sms() {
@@ -112,8 +108,7 @@ inline int gemm_num_sms() {
 
 template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
-                               const CUtensorMap* tout = nullptr, const CUtensorMap* ta_half = nullptr,
-                               const CUtensorMap* tb_half = nullptr, int max_ctas = 0) {
+                               const CUtensorMap* tout = nullptr, int max_ctas = 0) {
   using L = GemmSmem<BLOCK_N, kStages, kCta>;
   auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi, kCta>;
   static bool configured[64] = {};
@@ -132,7 +127,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, Gem
   grid = (grid / kCta) * kCta;
   if (tiles * kCta < grid) grid = tiles * kCta;
   if constexpr (kCta == 1) {
-    kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, ta_half ? *ta_half : ta, tb_half ? *tb_half : tb, p);
+    kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, p);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg{};
@@ -147,7 +142,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, Gem
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, ta_half ? *ta_half : ta, tb_half ? *tb_half : tb, p);
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, p);
   }
 }
 

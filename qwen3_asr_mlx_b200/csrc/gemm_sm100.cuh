@@ -59,7 +59,6 @@ struct GemmParams {
   int conv_kc_per_tap;     // K blocks per filter tap (ceil(C / 64))
   int conv_chunks;         // number of real chunks
   int a_tx_bytes;          // bytes one A-operand TMA box delivers (0 -> full stage: 128 rows x 128 B)
-  int conv_half_tail;      // 1: the last K block of every tap is 32 channels wide (64-byte rows, SWIZZLE_64B maps)
   // EPI_CONV_PLANES destination geometry
   int out_Hp, out_Wp;             // padded rows per chunk / padded width of destination planes
   long long out_plane_stride;     // elements between destination planes
@@ -98,8 +97,7 @@ constexpr bool epi_is_bf16() {
 template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_a_half,
-                const __grid_constant__ CUtensorMap tmap_b_half, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using L = GemmSmem<BLOCK_N, kStages, kCta>;
   static_assert(kCta == 1 || kCta == 2, "cta_group must be 1 or 2");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "invalid UMMA N");
@@ -168,11 +166,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           void* sa = smem_a + stage * L::kABytes;
           void* sb = smem_b + stage * L::kBBytes;
           if constexpr (kCta == 1) {
-            uint32_t tx = a_tx + L::kBBytes;
-            if constexpr (kAMode == A_CONV) {
-              if (p.conv_half_tail && (kb % p.conv_kc_per_tap) == p.conv_kc_per_tap - 1) tx >>= 1;  // 64-byte rows
-            }
-            ptx::mbar_expect_tx(&full_bar[stage], tx);
+            ptx::mbar_expect_tx(&full_bar[stage], a_tx + L::kBBytes);
             if constexpr (kAMode == A_ROWS) {
               ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
               ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, b_row0);
@@ -182,18 +176,13 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               const int kh = tap / 3, kw = tap - kh * 3;
               const int plane = 2 * (kh != 1) + (kw != 1);
               const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
-              const bool half_blk = p.conv_half_tail && kc == p.conv_kc_per_tap - 1;
-              ptx::tma_load_4d(sa, half_blk ? &tmap_a_half : &tmap_a, &full_bar[stage], kc * kBlockK, (kw != 0), row0, plane);
-              ptx::tma_load_3d(sb, half_blk ? &tmap_b_half : &tmap_b, &full_bar[stage], kc * kBlockK, tap, b_row0);
+              ptx::tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * kBlockK, (kw != 0), row0, plane);
+              ptx::tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBlockK, tap, b_row0);
             }
           } else {
             // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the pair
             const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
-            uint32_t tx = 2 * (a_tx + L::kBBytes);
-            if constexpr (kAMode == A_CONV) {
-              if (p.conv_half_tail && (kb % p.conv_kc_per_tap) == p.conv_kc_per_tap - 1) tx >>= 1;  // 64-byte rows
-            }
-            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
+            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (a_tx + L::kBBytes));
             if constexpr (kAMode == A_ROWS) {
               ptx::tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * kBlockK, m_blk * kBlockM);
               ptx::tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * kBlockK, b_row0);
@@ -203,9 +192,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               const int kh = tap / 3, kw = tap - kh * 3;
               const int plane = 2 * (kh != 1) + (kw != 1);
               const int row0 = m_blk * p.conv_rows_per_tile + (kh != 0);
-              const bool half_blk = p.conv_half_tail && kc == p.conv_kc_per_tap - 1;
-              ptx::tma_load_4d_cg2(sa, half_blk ? &tmap_a_half : &tmap_a, lead_bar, kc * kBlockK, (kw != 0), row0, plane);
-              ptx::tma_load_3d_cg2(sb, half_blk ? &tmap_b_half : &tmap_b, lead_bar, kc * kBlockK, tap, b_row0);
+              ptx::tma_load_4d_cg2(sa, &tmap_a, lead_bar, kc * kBlockK, (kw != 0), row0, plane);
+              ptx::tma_load_3d_cg2(sb, &tmap_b, lead_bar, kc * kBlockK, tap, b_row0);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -227,21 +215,12 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          bool half_blk = false;
-          if constexpr (kAMode == A_CONV) half_blk = p.conv_half_tail && (kb % p.conv_kc_per_tap) == p.conv_kc_per_tap - 1;
-          if (!half_blk) {
-            const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
-            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-              ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            }
-          } else {  // 32-channel tail block of a tap: 64-byte rows written with SWIZZLE_64B
-            const uint64_t adesc = ptx::make_sw64_kmajor_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
-            const uint64_t bdesc = ptx::make_sw64_kmajor_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
-#pragma unroll
-            for (int k = 0; k < 2; ++k) ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
+            ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (kCta == 1) ptx::umma_commit(&empty_bar[stage]);

@@ -26,7 +26,7 @@ constexpr int kMelBins = 128;
 constexpr int kMelFreqs = 201;
 constexpr int kMelMaxTaps = 12;       // max non-zeros per filter row we store (reference: <= 9)
 constexpr int kMelFramesPerCta = 32;
-constexpr int kMelThreads = 256;
+constexpr int kMelThreads = 288;      // 9 warps: the 32 x 9 DFT-25 tasks of a tile take exactly one round
 
 struct MelTables {
   const float* window;     // [400]  symmetric Hann, float32 (np.hanning(400).astype(f32))
@@ -115,12 +115,17 @@ __device__ __forceinline__ int upper_segment(const T* __restrict__ offs, int B, 
 }
 
 struct MelSmem {
-  float raw[(kMelFramesPerCta - 1) * kMelHop + kMelNfft];  // 5360
+  union {  // the raw samples are dead once step A has produced Y; the power spectrum is written in step C
+    float raw[(kMelFramesPerCta - 1) * kMelHop + kMelNfft];  // 5360
+    float P[kMelFreqs][kMelFramesPerCta + 1];
+  };
   float window[kMelNfft];
   float2 twiddle[9 * 25];
   float2 Y[kMelFramesPerCta][9][25];
-  float P[kMelFreqs][kMelFramesPerCta + 1];
-  float red[kMelThreads / 32];
+  float fb_weight[kMelBins * kMelMaxTaps];
+  short fb_start[kMelBins];
+  short fb_count[kMelBins];
+  float red[(kMelThreads + 31) / 32];
 };
 
 __global__ void __launch_bounds__(kMelThreads)
@@ -140,15 +145,34 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   const int nf = min(kMelFramesPerCta, T - t0);
 
   // ---- stage tables and the reflect-padded sample span of these frames
-  for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
-  for (int i = tid; i < 9 * 25; i += kMelThreads) s.twiddle[i] = __ldg(tab.twiddle + i);
   const int span = (nf - 1) * kMelHop + kMelNfft;
   const long long first = static_cast<long long>(t0) * kMelHop - kMelNfft / 2;
   const float* __restrict__ x = audio + s0;
-  for (int i = tid; i < span; i += kMelThreads) {
-    long long j = first + i;
-    if (j < 0 || j >= N) j = reflect_index(j, N);
-    s.raw[i] = __ldg(x + j);
+  if (first >= 0 && first + span <= N) {
+    // interior tile (the common case): no reflection, 8 independent loads in flight per thread
+    const float* __restrict__ src = x + first;
+    int i = tid;
+    for (; i + 7 * kMelThreads < span; i += 8 * kMelThreads) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i + u * kMelThreads);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s.raw[i + u * kMelThreads] = v[u];
+    }
+    for (; i < span; i += kMelThreads) s.raw[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < span; i += kMelThreads) {
+      long long j = first + i;
+      if (j < 0 || j >= N) j = reflect_index(j, N);
+      s.raw[i] = __ldg(x + j);
+    }
+  }
+  for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
+  for (int i = tid; i < 9 * 25; i += kMelThreads) s.twiddle[i] = __ldg(tab.twiddle + i);
+  for (int i = tid; i < kMelBins * kMelMaxTaps; i += kMelThreads) s.fb_weight[i] = __ldg(tab.fb_weight + i);
+  for (int i = tid; i < kMelBins; i += kMelThreads) {
+    s.fb_start[i] = static_cast<short>(__ldg(tab.fb_start + i));
+    s.fb_count[i] = static_cast<short>(__ldg(tab.fb_count + i));
   }
   __syncthreads();
 
@@ -196,11 +220,12 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   for (int task = tid; task < kMelBins * kMelFramesPerCta; task += kMelThreads) {
     const int m = task / kMelFramesPerCta, f = task - m * kMelFramesPerCta;
     if (f < nf) {
-      const int st = __ldg(tab.fb_start + m), cnt = __ldg(tab.fb_count + m);
-      const float* __restrict__ w = tab.fb_weight + m * kMelMaxTaps;
+      const int st = s.fb_start[m], cnt = s.fb_count[m];  // warp-uniform (one mel bin per warp pass)
+      const float* w = s.fb_weight + m * kMelMaxTaps;
       float acc = 0.0f;
-      for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), s.P[st + j][f], acc);
-      const float v = log10f(fmaxf(acc, 1e-10f));
+      for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], s.P[st + j][f], acc);
+      // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here
+      const float v = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
       out[static_cast<long long>(m) * T + t0 + f] = v;
       lmax = fmaxf(lmax, v);
     }
@@ -212,7 +237,7 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   if (tid == 0) {
     float m = s.red[0];
 #pragma unroll
-    for (int i = 1; i < kMelThreads / 32; ++i) m = fmaxf(m, s.red[i]);
+    for (int i = 1; i < (kMelThreads + 31) / 32; ++i) m = fmaxf(m, s.red[i]);
     atomicMax(utt_max + u, float_to_ordered(m));
   }
 }

@@ -58,7 +58,6 @@ struct DevBuf {
 // (each CTA loads half of the B rows: box = BLOCK_N / 2 rows).
 struct WeightMaps {
   CUtensorMap m1, m2;
-  CUtensorMap h1, h2;  // conv only: 32-channel tail-block maps (SWIZZLE_64B)
 };
 
 struct LayerWeights {
@@ -77,10 +76,6 @@ struct qasr_handle {
   bool finalized = false;
   bool debug = false;
   bool conv1_fp32 = false;  // QASR_CONV1_FP32=1 selects the CUDA-core fp32-weight conv1 (A/B testing)
-  // QASR_CONV_HALF_TAIL=1: make the 8th K block of every conv tap a 32-channel (64-byte-row, SWIZZLE_64B) block instead of
-  // zero-padding 480 -> 512 channels.  Saves 6.7 % of the MMA work but measured 30 % SLOWER on B200 (conv2 5.4 -> 6.9 ms):
-  // kept as a tested experiment, off by default.
-  int conv_half_tail = 0;
   bool attn_tc = true;      // QASR_ATTN_TC=0 selects the mma.sync attention kernel instead of the tcgen05 one
   bool cta_pair = true;     // QASR_CTA_PAIR=0 selects the single-CTA (cta_group::1) GEMM kernels
   qasr_stats stats{};
@@ -112,7 +107,6 @@ struct qasr_handle {
   DevBuf dbg_stem, dbg_layer0, dbg_hidden;
   long long dbg_tokens = 0;
   CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1, tm_qkv;
-  CUtensorMap tm_planes1_half, tm_planes2_half;
   // per-category CUDA-event profiling (qasr_set_profile)
   bool profile = false;
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
@@ -320,8 +314,7 @@ int build_weight_maps(qasr_handle* h) {
     return make_tmap_rows(&m.m1, w, n, k, k, 256, &e) && make_tmap_rows(&m.m2, w, n, k, k, 128, &e);
   };
   auto conv = [&](WeightMaps& m, const void* w) {
-    return make_tmap_conv_w(&m.m1, w, kStemC, kStemC, 240, &e) && make_tmap_conv_w(&m.m2, w, kStemC, kStemC, 120, &e) &&
-           make_tmap_conv_w(&m.h1, w, kStemC, kStemC, 240, &e, true) && make_tmap_conv_w(&m.h2, w, kStemC, kStemC, 120, &e, true);
+    return make_tmap_conv_w(&m.m1, w, kStemC, kStemC, 240, &e) && make_tmap_conv_w(&m.m2, w, kStemC, kStemC, 120, &e);
   };
   bool ok = conv(h->tm_conv2_w, h->conv2_w) && conv(h->tm_conv3_w, h->conv3_w) &&
             rows(h->tm_convout_w, h->convout_w, D, 16 * kStemC) && rows(h->tm_proj1_w, h->proj1_w, D, D) &&
@@ -351,8 +344,6 @@ int ensure_workspace(qasr_handle* h, long long tokens, long long chunks, long lo
     if ((rc = dev_alloc(h, h->flat3, static_cast<size_t>(G) * 13 * 16 * kStemC * 2, true))) return rc;
     if (!make_tmap_conv_act(&h->tm_planes1, h->planes1.p, kStemC, 26, G * 33, 25, 5, &e)) return fail(h, QASR_ERR_CUDA, e);
     if (!make_tmap_conv_act(&h->tm_planes2, h->planes2.p, kStemC, 14, G * 17, 13, 9, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_conv_act(&h->tm_planes1_half, h->planes1.p, kStemC, 26, G * 33, 25, 5, &e, true)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_conv_act(&h->tm_planes2_half, h->planes2.p, kStemC, 14, G * 17, 13, 9, &e, true)) return fail(h, QASR_ERR_CUDA, e);
     if (!make_tmap_rows(&h->tm_flat3, h->flat3.p, G * 13, 16 * kStemC, 16 * kStemC, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
     h->cap_group = G;
   }
@@ -610,10 +601,9 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
       p.out = h->planes2.p; p.bias = h->conv2_b;
       p.out_Hp = 17; p.out_Wp = 14; p.out_plane_stride = ps2; p.out_C = kStemC;
-      p.conv_half_tail = h->conv_half_tail;
       ProfScope ps(h, QASR_PROF_CONV2, st, 2.0 * 32 * 25 * kStemC * 9 * kStemC * g, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_PLANES, 2>(h->tm_planes1, h->tm_conv2_w.m2, p, st, nullptr, &h->tm_planes1_half, &h->tm_conv2_w.h2)));
-      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES, 1>(h->tm_planes1, h->tm_conv2_w.m1, p, st, nullptr, &h->tm_planes1_half, &h->tm_conv2_w.h1)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_PLANES, 2>(h->tm_planes1, h->tm_conv2_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES, 1>(h->tm_planes1, h->tm_conv2_w.m1, p, st)));
     }
     {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
       GemmParams p{};
@@ -623,10 +613,9 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       p.num_m_tiles = (g * 17 + 8) / 9;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
       p.out = h->flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
-      p.conv_half_tail = h->conv_half_tail;
       ProfScope ps(h, QASR_PROF_CONV3, st, 2.0 * 16 * 13 * kStemC * 9 * kStemC * g, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_FLAT, 2>(h->tm_planes2, h->tm_conv3_w.m2, p, st, nullptr, &h->tm_planes2_half, &h->tm_conv3_w.h2)));
-      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT, 1>(h->tm_planes2, h->tm_conv3_w.m1, p, st, nullptr, &h->tm_planes2_half, &h->tm_conv3_w.h1)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_FLAT, 2>(h->tm_planes2, h->tm_conv3_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT, 1>(h->tm_planes2, h->tm_conv3_w.m1, p, st)));
     }
     {  // conv_out + positional embedding + strip padding + pack (encoder.py:277-293)
       GemmParams p = dense_params(g * kTokensPerChunk, D, 16 * kStemC, x, D, nullptr);
@@ -727,7 +716,6 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   if (const char* c1 = getenv("QASR_CONV1_FP32")) h->conv1_fp32 = atoi(c1) != 0;
   if (const char* cp = getenv("QASR_CTA_PAIR")) h->cta_pair = atoi(cp) != 0;
   if (const char* at = getenv("QASR_ATTN_TC")) h->attn_tc = atoi(at) != 0;
-  if (const char* ht = getenv("QASR_CONV_HALF_TAIL")) h->conv_half_tail = atoi(ht) != 0;
   if (const char* sg = getenv("QASR_STEM_GROUP")) {
     const int v = atoi(sg);
     if (v > 0) h->stem_group = v;

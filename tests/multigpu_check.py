@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from qwen3_asr_mlx_b200 import AudioEncoder, AudioEncoderConfig, launcher, weights  # noqa: E402
-from tests.helpers import synth  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import synth  # noqa: E402
 
 
 def main():

@@ -149,9 +149,9 @@ def test_stem_grouping_is_transparent(small, monkeypatch):
     enc2.close()
 
 
-@pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CONV_HALF_TAIL": "1"}, {"QASR_CONV1_FP32": "1"},
-                                 {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_CONV_HALF_TAIL": "1", "QASR_GRAPHS": "0"}],
-                         ids=["single_cta_gemm", "mma_sync_attention", "conv_half_tail_block", "conv1_cuda_cores_fp32_weights", "all_alternative_kernels_eager"])
+@pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CONV1_FP32": "1"},
+                                 {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_GRAPHS": "0"}],
+                         ids=["single_cta_gemm", "mma_sync_attention", "conv1_cuda_cores_fp32_weights", "all_alternative_kernels_eager"])
 def test_kernel_variants_agree(small, monkeypatch, env):
     """The alternative kernels (cta_group::1 GEMM, mma.sync attention, eager launches) give the same
     embeddings as the default configuration (cta_group::2 GEMM, tcgen05 attention, graph replay)."""
