@@ -151,6 +151,11 @@ int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_
 int qasr_test_gemm(int device, const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, int32_t M,
                    int32_t N, int32_t K, int32_t mode, float* out);
 
+/* Micro-benchmark of the dense tcgen05 GEMM on device-resident pseudo-random bf16 operands (CUDA-event timed, back to back).
+ * mode: 0 bf16 store, 1 bias+GELU bf16 store, 2 fp32 residual (TMA reduce-add), 3 accumulators discarded (main-loop ceiling);
+ * +16 selects the CTA-pair kernel. */
+int qasr_bench_gemm(int device, int32_t M, int32_t N, int32_t K, int32_t mode, int32_t iters, float* ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

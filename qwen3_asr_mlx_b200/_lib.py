@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint16, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqasr.so")
+LIB_PATH = os.environ.get("QASR_LIB_PATH") or os.path.join(_HERE, "lib", "libqasr.so")  # override: A/B builds
 
 QASR_F32 = 0
 QASR_BF16 = 1
@@ -83,6 +83,7 @@ _SIGNATURES = {
     "qasr_profile_name": (c_char_p, [c_int]),
     "qasr_set_debug": (c_int, [c_void_p, c_int]),
     "qasr_debug_read": (c_int, [c_void_p, c_char_p, POINTER(c_float), c_size_t]),
+    "qasr_bench_gemm": (c_int, [c_int, c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
     "qasr_test_gemm": (c_int, [c_int, POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
 }
 
@@ -105,6 +106,8 @@ def load() -> ctypes.CDLL:
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if os.environ.get("QASR_LIB_PATH") and not hasattr(lib, name):
+            continue  # A/B build of an older revision: tolerate symbols it does not have yet
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args

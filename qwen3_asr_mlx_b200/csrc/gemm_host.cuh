@@ -106,11 +106,11 @@ inline int gemm_num_sms() {
   return v;
 }
 
-template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1>
+template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1, bool kDbg = false>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
                                const CUtensorMap* tout = nullptr, int max_ctas = 0) {
   using L = GemmSmem<BLOCK_N, kStages, kCta>;
-  auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi, kCta>;
+  auto kern = gemm_bf16_sm100<BLOCK_N, kStages, kAMode, kEpi, kCta, kDbg>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

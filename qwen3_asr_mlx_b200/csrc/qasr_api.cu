@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -453,7 +454,8 @@ int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, 
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
   CUtensorMap tout;
   const CUtensorMap* toutp = nullptr;
-  if (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {  // fp32 outputs leave through a TMA store / reduce (exact row count: rows >= M are clipped)
+  // dense outputs leave through a TMA tile store / reduce (exact row count: rows >= M are clipped by the map)
+  if (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
     std::string e;
     if (!make_tmap_out_f32(&tout, out, M, N, ldo, &e)) return fail(h, QASR_ERR_CUDA, e);
     toutp = &tout;
@@ -1262,6 +1264,92 @@ int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_
   if (n_floats > have) return fail(h, QASR_ERR_INVALID, "debug buffer smaller than requested");
   QCUDA(h, cudaDeviceSynchronize());
   QCUDA(h, cudaMemcpy(host_out, b->p, n_floats * 4, cudaMemcpyDeviceToHost));
+  return QASR_OK;
+}
+
+int qasr_bench_gemm(int device, int32_t M, int32_t N, int32_t K, int32_t mode, int32_t iters, float* ms_per_launch) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0 || iters <= 0 || !ms_per_launch)
+    return fail(nullptr, QASR_ERR_INVALID, "qasr_bench_gemm: bad argument");
+  qasr_handle* h = nullptr;
+  QCUDA(h, cudaSetDevice(device));
+  const bool pair = (mode & 16) != 0;
+  const bool dbg = getenv("QASR_GEMM_DBG") != nullptr;  // instrumented instantiations (cta_group::2 only)
+  const int epi = mode & 15;
+  void *da = nullptr, *dw = nullptr, *dout = nullptr, *db = nullptr;
+  long long* ddbg = nullptr;
+  QCUDA(h, cudaMalloc(&da, static_cast<size_t>(M) * K * 2));
+  QCUDA(h, cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
+  QCUDA(h, cudaMalloc(&dout, static_cast<size_t>(M) * N * 4));
+  QCUDA(h, cudaMalloc(&db, static_cast<size_t>(N) * 4));
+  QCUDA(h, cudaMalloc(&ddbg, 256 * 4 * sizeof(long long)));
+  QCUDA(h, cudaMemset(ddbg, 0, 256 * 4 * sizeof(long long)));
+  {  // bf16 pattern with realistic bit toggling (all-zero operands would flatter the power draw)
+    std::vector<uint16_t> pat(1 << 20);
+    uint32_t s = 12345u;
+    for (auto& v : pat) { s = s * 1664525u + 1013904223u; v = f32_to_bf16(((s >> 8) & 0xFFFF) / 32768.0f - 1.0f); }
+    for (size_t off = 0; off < static_cast<size_t>(M) * K; off += pat.size())
+      QCUDA(h, cudaMemcpy(static_cast<uint16_t*>(da) + off, pat.data(), std::min(pat.size(), static_cast<size_t>(M) * K - off) * 2, cudaMemcpyHostToDevice));
+    for (size_t off = 0; off < static_cast<size_t>(N) * K; off += pat.size())
+      QCUDA(h, cudaMemcpy(static_cast<uint16_t*>(dw) + off, pat.data(), std::min(pat.size(), static_cast<size_t>(N) * K - off) * 2, cudaMemcpyHostToDevice));
+  }
+  QCUDA(h, cudaMemset(dout, 0, static_cast<size_t>(M) * N * 4));
+  QCUDA(h, cudaMemset(db, 0, static_cast<size_t>(N) * 4));
+  CUtensorMap ta, tw, tout;
+  std::string e;
+  if (!make_tmap_rows(&ta, da, M, K, K, kBlockM, &e) || !make_tmap_rows(&tw, dw, N, K, K, pair ? 128 : 256, &e) ||
+      !make_tmap_out_f32(&tout, dout, M, N, N, &e))
+    return fail(nullptr, QASR_ERR_CUDA, e);
+  GemmParams p = dense_params(M, N, K, dout, N, static_cast<const float*>(db));
+  p.row_map = reinterpret_cast<const int*>(ddbg);  // counter buffer of the instrumented instantiations
+  auto launch = [&]() -> cudaError_t {
+    if (pair && dbg) {
+      switch (epi) {
+        case 0: return launch_gemm<256, kPairStages, A_ROWS, EPI_STORE_BF16, 2, true>(ta, tw, p, 0);
+        case 1: return launch_gemm<256, kPairStages, A_ROWS, EPI_GELU_BF16, 2, true>(ta, tw, p, 0);
+        case 2: return launch_gemm<256, kPairStages, A_ROWS, EPI_RESID_F32, 2, true>(ta, tw, p, 0, &tout);
+        case 4: return launch_gemm<256, kPairStages, A_ROWS, EPI_MATH_ONLY, 2, true>(ta, tw, p, 0);
+        default: return launch_gemm<256, kPairStages, A_ROWS, EPI_DISCARD, 2, true>(ta, tw, p, 0);
+      }
+    }
+    if (pair) {
+      switch (epi) {
+        case 0: return launch_gemm<256, kPairStages, A_ROWS, EPI_STORE_BF16, 2>(ta, tw, p, 0);
+        case 1: return launch_gemm<256, kPairStages, A_ROWS, EPI_GELU_BF16, 2>(ta, tw, p, 0);
+        case 2: return launch_gemm<256, kPairStages, A_ROWS, EPI_RESID_F32, 2>(ta, tw, p, 0, &tout);
+        case 4: return launch_gemm<256, kPairStages, A_ROWS, EPI_MATH_ONLY, 2>(ta, tw, p, 0);
+        default: return launch_gemm<256, kPairStages, A_ROWS, EPI_DISCARD, 2>(ta, tw, p, 0);
+      }
+    }
+    switch (epi) {
+      case 0: return launch_gemm<256, kGemmStages, A_ROWS, EPI_STORE_BF16, 1>(ta, tw, p, 0);
+      case 1: return launch_gemm<256, kGemmStages, A_ROWS, EPI_GELU_BF16, 1>(ta, tw, p, 0);
+      case 2: return launch_gemm<256, kGemmStages, A_ROWS, EPI_RESID_F32, 1>(ta, tw, p, 0, &tout);
+      default: return launch_gemm<256, kGemmStages, A_ROWS, EPI_DISCARD, 1>(ta, tw, p, 0);
+    }
+  };
+  for (int i = 0; i < 3; ++i) QCUDA(h, launch());
+  cudaEvent_t e0, e1;
+  QCUDA(h, cudaEventCreate(&e0));
+  QCUDA(h, cudaEventCreate(&e1));
+  QCUDA(h, cudaDeviceSynchronize());
+  QCUDA(h, cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) QCUDA(h, launch());
+  QCUDA(h, cudaEventRecord(e1, 0));
+  QCUDA(h, cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  QCUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_launch = ms / iters;
+  if (pair && dbg) {
+    std::vector<long long> hd(256 * 4);
+    QCUDA(h, cudaMemcpy(hd.data(), ddbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int b : {0, 74}) {
+      const long long* d = hd.data() + b * 4;
+      fprintf(stderr, "  cta %3d: mma thread total %lld cyc, waiting for a free accumulator %lld, waiting for smem stages %lld, tiles %lld\n", b,
+              d[0], d[1], d[2], d[3]);
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(da); cudaFree(dw); cudaFree(dout); cudaFree(db); cudaFree(ddbg);
   return QASR_OK;
 }
 
