@@ -313,6 +313,14 @@ def main():
         d_n = sum(prof[k]["launches"] for k in dense)
         total_ms = sum(v["ms"] for v in prof.values())
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
+        # DRAM traffic per launch of the same kernel family, from the committed ncu --set full capture (launch-weighted mean)
+        dense_traffic, traffic_by_kernel = None, {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic_by_kernel = json.load(open(tpath)).get("bytes_per_launch", {})
+            have = [k for k in dense if k in traffic_by_kernel and prof[k]["launches"] > 0]
+            if have:
+                dense_traffic = sum(traffic_by_kernel[k] * prof[k]["launches"] for k in have) / sum(prof[k]["launches"] for k in have)
         peak = peaks["bf16_tflops_sustained"]
         kernels = {}
         for k, v in prof.items():
@@ -325,6 +333,8 @@ def main():
             if v["bytes"] > 0 and v["flops"] == 0 or k in ("conv1",):
                 ent["gbs"] = v["bytes"] / (v["ms"] / 1e3) / 1e9
                 ent["frac_hbm_peak"] = ent["gbs"] / peaks["hbm_gbs"]
+            if k in traffic_by_kernel:
+                ent["ncu_dram_bytes_per_launch"] = traffic_by_kernel[k]
             kernels[k] = ent
         roofline = {
             "kernel": "gemm_bf16_sm100<256,4,A_ROWS,*> (tcgen05 dense GEMM: qkv/out_proj/fc1/fc2/projector/conv_out)",
@@ -334,7 +344,8 @@ def main():
             "timing": "CUDA-event pair around every launch on the launch stream, second pass of the same K steps (eager; the timed pass replays a CUDA graph)",
             "profiled_pass_ms_per_step": profiled_ms_per_step, "sum_of_kernels_ms_per_step": total_ms / args.steps,
             "algorithmic_flops_per_launch": d_fl / max(d_n, 1),
-            "traffic": None,
+            "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram bytes read+written per launch, launch-weighted over the family)",
+            "traffic": dense_traffic,
             "whole_step_tflops": FLOP_PER_UTT * UTTS_PER_GPU / (ms_per_step / 1e3) / 1e12,
             "whole_step_frac": FLOP_PER_UTT * UTTS_PER_GPU / (ms_per_step / 1e3) / 1e12 / peak,
         }

@@ -145,9 +145,10 @@ class AudioEncoder:
                                   ctypes.c_void_p(out.data_ptr()), cdt, runtime.i64_ptr(toffs), h.stream_ptr()))
         return DeviceArray(out), toffs
 
-    def encode_audio_batch(self, audios: Sequence, out_dtype: str = "float32") -> Tuple[DeviceArray, np.ndarray]:
+    def encode_audio_batch(self, audios: Sequence, out_dtype: str = "float32", max_tokens_per_call: int = 65536) -> Tuple[DeviceArray, np.ndarray]:
         """Waveforms in, packed embeddings out: mel + encoder back to back on the device
-        (the reference call site model.py:331-335, batched)."""
+        (the reference call site model.py:331-335, batched).  Batches larger than ``max_tokens_per_call``
+        audio tokens are processed in consecutive sub-batches so the activation workspace stays bounded."""
         self._ensure_weights()
         h = self._handle
         waves = [_as_waveform(a, SAMPLE_RATE) for a in audios]
@@ -157,6 +158,23 @@ class AudioEncoder:
         for n in lengths:
             if n < HOP_LENGTH:
                 raise ValueError(f"zero-size array to reduction operation maximum which has no identity (audio of {n} samples < {HOP_LENGTH})")
+        tokens = [self.num_tokens(n // HOP_LENGTH) for n in lengths]
+        if sum(tokens) > max_tokens_per_call and len(waves) > 1:
+            pieces, offsets, cur, acc = [], [0], [], 0
+            for w, t in zip(waves, tokens):
+                if cur and acc + t > max_tokens_per_call:
+                    emb, toffs = self.encode_audio_batch(cur, out_dtype, max_tokens_per_call=1 << 62)
+                    pieces.append(emb.tensor)
+                    base = offsets[-1]
+                    offsets.extend(base + int(v) for v in toffs[1:])
+                    cur, acc = [], 0
+                cur.append(w)
+                acc += t
+            emb, toffs = self.encode_audio_batch(cur, out_dtype, max_tokens_per_call=1 << 62)
+            pieces.append(emb.tensor)
+            base = offsets[-1]
+            offsets.extend(base + int(v) for v in toffs[1:])
+            return DeviceArray(torch.cat(pieces)), np.asarray(offsets, dtype=np.int64)
         soffs = runtime.offsets_array(lengths)
         with torch.cuda.device(h.torch_device):
             if len(waves) == 1:

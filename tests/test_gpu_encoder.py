@@ -124,6 +124,17 @@ def test_varlen_batch_equals_loop_of_singles(small):
         assert rel_err(single, encoder_torch.encoder_forward(params, cfg, m)) <= EMB_TOL
 
 
+def test_sub_batching_is_transparent(small):
+    """encode_audio_batch splits oversize batches into workspace-bounded sub-batches; results are unchanged."""
+    cfg, params, enc = small
+    rng = np.random.default_rng(17)
+    xs = [synth(rng, int(n)) for n in rng.integers(4000, 120000, size=11)]
+    whole, offs = enc.encode_audio_batch(xs)
+    split, offs2 = enc.encode_audio_batch(xs, max_tokens_per_call=150)
+    assert list(offs) == list(offs2)
+    assert np.array_equal(np.array(whole), np.array(split))
+
+
 def test_windows_are_independent(small):
     """Block-diagonal attention without a mask tensor: tokens of the first 8-s window do not depend on later audio."""
     cfg, params, enc = small
