@@ -126,6 +126,14 @@ int qasr_encode_audio_host_async(qasr_handle* h, int32_t slot, const float* audi
                                  int32_t batch, void* emb_host, int out_dtype, int64_t* token_offsets_out);
 int qasr_host_wait(qasr_handle* h, int32_t slot);
 
+/* Prompt assembly, the consumer of this path (reference prepare_inputs, src/qwen3_asr_mlx/generate.py:20-81):
+ * out[t] = embed_table[input_ids[t]], except at audio_pad_id positions, where out[t] = the next audio embedding row cast to
+ * the table dtype.  input_ids is a HOST array; tables / embeddings / out are device pointers; out has n_ids x hidden elements of
+ * table_dtype.  A pad count different from n_audio (and from 0) is QASR_ERR_INVALID, like the reference's ValueError. */
+int qasr_prepare_inputs(qasr_handle* h, const int32_t* input_ids, int64_t n_ids, const void* embed_table_dev, int table_dtype,
+                        int64_t vocab, int32_t hidden, const void* audio_emb_dev, int audio_dtype, int64_t n_audio,
+                        int32_t audio_pad_id, void* out_dev, void* stream);
+
 /* ---- constant tables, as the library builds them (for parity tests) ---- */
 int qasr_mel_filterbank(float* out_128x201);
 int qasr_hann_window(float* out_400);

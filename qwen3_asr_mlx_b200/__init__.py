@@ -11,7 +11,9 @@ from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
 from .config import AudioEncoderConfig
 from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
 from ._array import DeviceArray
+from .generate import prepare_inputs
 from .model import LANGUAGE_MAP, Qwen3ASR, TranscriptionResult
+from .tokenizer import build_prompt
 
 __all__ = [
     "__version__",
@@ -26,4 +28,6 @@ __all__ = [
     "Qwen3ASR",
     "TranscriptionResult",
     "LANGUAGE_MAP",
+    "prepare_inputs",
+    "build_prompt",
 ]

@@ -134,6 +134,26 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+// ------------------------------------------------------------------------------ prompt assembly
+// prepare_inputs (reference generate.py:20-81): row t of the decoder input is the text-embedding row
+// of input_ids[t], except at <|audio_pad|> positions where it is the next audio embedding (cast to
+// the embedding dtype).  src[t] >= 0: audio row index; src[t] < 0: embedding-table row -(src[t]+1).
+template <typename TTable, typename TAudio>
+__global__ void __launch_bounds__(128)
+gather_prompt_rows_kernel(const int* __restrict__ src, const TTable* __restrict__ table, const TAudio* __restrict__ audio,
+                          TTable* __restrict__ out, int hidden) {
+  const long long t = blockIdx.x;
+  const int s = __ldg(src + t);
+  TTable* __restrict__ o = out + t * hidden;
+  if (s >= 0) {
+    const TAudio* __restrict__ a = audio + static_cast<long long>(s) * hidden;
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) o[i] = static_cast<TTable>(static_cast<float>(a[i]));
+  } else {
+    const TTable* __restrict__ r = table + static_cast<long long>(-(s + 1)) * hidden;
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) o[i] = r[i];
+  }
+}
+
 // ------------------------------------------------------------------------------ attention
 // One CTA per (window, head).  Window = up to 104 consecutive packed tokens of one utterance.
 // qkv: [n_tok, 3*D] bf16 (q | k | v), head h occupies columns h*64 .. h*64+63 of each third.

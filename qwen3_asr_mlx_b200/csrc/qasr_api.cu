@@ -105,7 +105,7 @@ struct qasr_handle {
   long long cap_io_in = 0, cap_io_out = 0;
   DevBuf planes1, planes2, flat3, x, xn, qkv, attn, hbuf, mel_scratch, io_in, io_out;
   DevBuf d_chunks, d_rowmap, d_windows, d_soffs, d_foffs, d_boffs, d_uttmax;
-  DevBuf dbg_stem, dbg_layer0, dbg_hidden;
+  DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src;
   long long dbg_tokens = 0;
   CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1, tm_qkv;
   // per-category CUDA-event profiling (qasr_set_profile)
@@ -752,7 +752,7 @@ void qasr_destroy(qasr_handle* h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->planes1, &h->planes2, &h->flat3, &h->x, &h->xn, &h->qkv, &h->attn, &h->hbuf, &h->mel_scratch,
                     &h->io_in, &h->io_out, &h->d_chunks, &h->d_rowmap, &h->d_windows, &h->d_soffs, &h->d_foffs,
-                    &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden};
+                    &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden, &h->d_prompt_src};
   for (DevBuf* b : bufs) dev_free(h, *b);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -1179,6 +1179,56 @@ int qasr_host_wait(qasr_handle* h, int32_t slot) {
   if (!h->slot_busy[slot]) return QASR_OK;
   QCUDA(h, cudaEventSynchronize(h->ev_done[slot]));
   h->slot_busy[slot] = false;
+  return QASR_OK;
+}
+
+int qasr_prepare_inputs(qasr_handle* h, const int32_t* input_ids, int64_t n_ids, const void* embed_table_dev, int table_dtype,
+                        int64_t vocab, int32_t hidden, const void* audio_emb_dev, int audio_dtype, int64_t n_audio,
+                        int32_t audio_pad_id, void* out_dev, void* stream) {
+  if (!h || !input_ids || n_ids <= 0 || !embed_table_dev || !out_dev || hidden <= 0 || vocab <= 0 || n_audio < 0 || n_ids > 0x7FFFFFFF)
+    return fail(h, QASR_ERR_INVALID, "qasr_prepare_inputs: bad argument");
+  if ((table_dtype != QASR_F32 && table_dtype != QASR_BF16) || (audio_dtype != QASR_F32 && audio_dtype != QASR_BF16))
+    return fail(h, QASR_ERR_INVALID, "bad dtype");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  std::vector<int> src(static_cast<size_t>(n_ids));
+  long long pads = 0;
+  for (int64_t t = 0; t < n_ids; ++t) {
+    const int id = input_ids[t];
+    if (id == audio_pad_id) src[t] = static_cast<int>(pads++);
+    else {
+      if (id < 0 || id >= vocab) return fail(h, QASR_ERR_INVALID, "token id out of range");
+      src[t] = -(id + 1);
+    }
+  }
+  // the reference returns the plain text embeddings when the prompt holds no audio pads (generate.py:55-56)
+  if (pads != 0 && pads != n_audio)
+    return fail(h, QASR_ERR_INVALID, "Number of audio-pad tokens (" + std::to_string(pads) + ") does not match encoder output length (" +
+                                         std::to_string(n_audio) + ").");
+  if (pads != 0 && !audio_emb_dev) return fail(h, QASR_ERR_INVALID, "null audio embeddings");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = dev_alloc(h, h->d_prompt_src, src.size() * sizeof(int), false))) return rc;
+  if ((rc = pin_begin(h, src.size() * sizeof(int) + 64))) return rc;
+  uint8_t* pin = pin_take(h, src.size() * sizeof(int));
+  if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
+  memcpy(pin, src.data(), src.size() * sizeof(int));
+  QCUDA(h, cudaMemcpyAsync(h->d_prompt_src.p, pin, src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if ((rc = pin_end(h, st))) return rc;
+  const int* dsrc = static_cast<const int*>(h->d_prompt_src.p);
+  const unsigned grid = static_cast<unsigned>(n_ids);
+  if (table_dtype == QASR_BF16) {
+    auto* tb = static_cast<const __nv_bfloat16*>(embed_table_dev);
+    auto* ob = static_cast<__nv_bfloat16*>(out_dev);
+    if (audio_dtype == QASR_F32) gather_prompt_rows_kernel<<<grid, 128, 0, st>>>(dsrc, tb, static_cast<const float*>(audio_emb_dev), ob, hidden);
+    else gather_prompt_rows_kernel<<<grid, 128, 0, st>>>(dsrc, tb, static_cast<const __nv_bfloat16*>(audio_emb_dev), ob, hidden);
+  } else {
+    auto* tf = static_cast<const float*>(embed_table_dev);
+    auto* of = static_cast<float*>(out_dev);
+    if (audio_dtype == QASR_F32) gather_prompt_rows_kernel<<<grid, 128, 0, st>>>(dsrc, tf, static_cast<const float*>(audio_emb_dev), of, hidden);
+    else gather_prompt_rows_kernel<<<grid, 128, 0, st>>>(dsrc, tf, static_cast<const __nv_bfloat16*>(audio_emb_dev), of, hidden);
+  }
+  QCUDA(h, cudaGetLastError());
+  h->stats.kernel_launches++;
   return QASR_OK;
 }
 

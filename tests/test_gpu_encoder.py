@@ -291,3 +291,54 @@ def test_full_arch_config2_size_properties(full):
     assert np.array_equal(single, e[780:1170])
     ref = encoder_torch.encoder_forward(params, cfg, mel_np.log_mel_spectrogram_fast(xs[2]))
     assert rel_err(single, ref) <= EMB_TOL
+
+
+def test_from_pretrained_local_checkpoint_and_shell(tmp_path, small):
+    """Qwen3ASR.from_pretrained on a local directory holding config.json + model.safetensors (audio_tower.* keys,
+    bf16, MLX layouts) -- reference model.py:151-188, encoder.py:330-359 -- and the transcribe() shell behaviour."""
+    import json
+
+    import torch
+    from safetensors.torch import save_file
+
+    from qwen3_asr_mlx_b200 import AudioEncoder, Qwen3ASR, TranscriptionResult
+
+    cfg, params, enc = small
+    tensors = {"audio_tower." + k: torch.from_numpy(v).to(torch.bfloat16) for k, v in params.items()}
+    tensors["model.embed_tokens.weight"] = torch.zeros(4, 4, dtype=torch.bfloat16)  # decoder tensors are ignored
+    save_file(tensors, str(tmp_path / "model.safetensors"))
+    (tmp_path / "config.json").write_text(json.dumps({"audio_encoder_config": {
+        "d_model": cfg.d_model, "encoder_layers": cfg.encoder_layers, "encoder_attention_heads": cfg.encoder_attention_heads,
+        "encoder_ffn_dim": cfg.encoder_ffn_dim, "output_dim": cfg.output_dim}}))
+    x = synth(np.random.default_rng(5), 16000 * 3 + 123)
+
+    seen = {}
+
+    def fake_decoder(audio_embeddings, n_audio_tokens, language, max_tokens, **sampling):
+        seen["n"] = n_audio_tokens
+        seen["shape"] = audio_embeddings.shape
+        seen["language"] = language
+        return " hello "
+
+    with Qwen3ASR.from_pretrained(tmp_path, decoder_backend=fake_decoder) as model:
+        emb = np.array(model.encode(x))
+        # same weights (rounded to bf16 by the checkpoint) loaded directly
+        ref_enc = AudioEncoder(cfg)
+        ref_enc.load_weights({k: bf16_round(v) for k, v in params.items()})
+        assert np.array_equal(emb[0], np.array(ref_enc.encode_audio_batch([x])[0]))
+        ref_enc.close()
+        assert emb.shape == (1, enc.num_tokens(len(x) // 160), cfg.output_dim)
+        r = model.transcribe(x, language="de")
+        assert isinstance(r, TranscriptionResult) and r.text == "hello" and r.language == "German" and abs(r.duration - len(x) / 16000) < 1e-9
+        assert seen["n"] == emb.shape[1] and seen["shape"] == (emb.shape[1], cfg.output_dim)
+        assert model.transcribe(np.zeros(0, dtype=np.float32)) == TranscriptionResult("", "Unknown", 0.0)  # model.py:303-304
+        with pytest.raises(ValueError):
+            model.transcribe(np.zeros((2, 16000), dtype=np.float32))  # model.py:298-301
+        # long audio: split at low-energy boundaries, every segment encoded in one varlen batch (model.py:382-447)
+        long = np.concatenate([x, np.zeros(8000, dtype=np.float32), x])
+        r = model.transcribe(long, chunk_duration=3.5)
+        assert r.text == "hello hello"
+        model.warm_up()
+    with Qwen3ASR.from_pretrained(tmp_path) as model:
+        with pytest.raises(NotImplementedError):
+            model.transcribe(x)
