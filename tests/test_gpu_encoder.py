@@ -230,6 +230,24 @@ def test_full_arch_config1_parity(full):
         assert rel_err(e[int(toffs[u]): int(toffs[u + 1])], r) <= EMB_TOL
 
 
+def test_full_arch_parity_with_upstream_implementation(full):
+    """CUDA path vs the model authors' PyTorch audio tower (transformers Qwen3OmniMoeAudioEncoder, fp32 on the
+    host), without going through oracle/: 12.5 s and 30 s of audio, full 24-layer 1.7B architecture."""
+    upstream_hf = pytest.importorskip("upstream_hf")
+    pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    cfg, params, enc = full
+    model = upstream_hf.build_upstream(cfg, params)
+    rng = np.random.default_rng(21)
+    xs = [synth(rng, n) for n in (200000, 480000)]
+    emb, toffs = enc.encode_audio_batch(xs)
+    e = np.array(emb)
+    for u, x in enumerate(xs):
+        up = upstream_hf.upstream_forward(model, mel_np.log_mel_spectrogram_fast(x))
+        got = e[int(toffs[u]): int(toffs[u + 1])]
+        assert got.shape == up.shape
+        assert rel_err(got, up) <= EMB_TOL
+
+
 def test_full_arch_host_entry_point(full):
     cfg, params, enc = full
     rng = np.random.default_rng(8)
