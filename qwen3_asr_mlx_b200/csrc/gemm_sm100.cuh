@@ -60,6 +60,7 @@ struct GemmParams {
   int conv_OHp;            // padded output rows per chunk (= OH + 1, the extra row is a dummy)
   int conv_rows_per_tile;  // output rows per M tile (rows_per_tile * OW <= 128)
   int conv_kc_per_tap;     // K blocks per filter tap (ceil(C / 64))
+  int conv_tail_k16;       // K=16 MMA steps that carry data in the LAST K block of a tap (C % 64 / 16, 0 -> all 4)
   int conv_chunks;         // number of real chunks
   int a_tx_bytes;          // bytes one A-operand TMA box delivers (0 -> full stage: 128 rows x 128 B)
   // EPI_CONV_PLANES destination geometry
@@ -222,6 +223,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if constexpr (kDbg) { t_wait_acc += clock64() - t0; ++t_tiles; }
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccumStride;
+        int kc = 0;  // K block within the current filter tap (A_CONV)
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           if constexpr (kDbg) t0 = clock64();
           ptx::mbar_wait(&full_bar[stage], phase);
@@ -229,10 +231,16 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
           const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
+          // The last K block of a conv tap is zero-filled beyond C channels (480 = 7.5 x 64): MMAs over the
+          // all-zero K=16 slices are skipped (they would add nothing and cost tensor-pipe time and power).
+          int nk = kBlockK / kUmmaK;
+          if constexpr (kAMode == A_CONV) {
+            if (++kc == p.conv_kc_per_tap) { kc = 0; if (p.conv_tail_k16 > 0) nk = p.conv_tail_k16; }
+          }
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-            ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (k < nk) ptx::umma_bf16_ss<kCta>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (kCta == 1) ptx::umma_commit(&empty_bar[stage]);

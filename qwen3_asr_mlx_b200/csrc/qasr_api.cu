@@ -68,6 +68,16 @@ struct LayerWeights {
   WeightMaps tm_wqkv, tm_wo, tm_w1, tm_w2;
 };
 
+// One encoder "lane": the activation workspace of an independent share of the batch.  A call whose batch is
+// large enough is split (at an utterance boundary) into two lanes that run on two streams, so that the
+// tail wave / memory-bound kernels of one lane overlap the tensor-bound kernels of the other.
+struct Lane {
+  long long cap_group = 0, cap_tokens = 0, cap_chunks = 0, cap_windows = 0;
+  DevBuf planes1, planes2, flat3, x, xn, qkv, attn, hbuf;
+  DevBuf d_chunks, d_rowmap, d_windows;
+  CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1, tm_qkv;
+};
+
 }  // namespace
 
 struct qasr_handle {
@@ -79,6 +89,7 @@ struct qasr_handle {
   bool conv1_fp32 = false;  // QASR_CONV1_FP32=1 selects the CUDA-core fp32-weight conv1 (A/B testing)
   bool attn_tc = true;      // QASR_ATTN_TC=0 selects the mma.sync attention kernel instead of the tcgen05 one
   bool cta_pair = true;     // QASR_CTA_PAIR=0 selects the single-CTA (cta_group::1) GEMM kernels
+  bool conv_tail_skip = true;  // QASR_CONV_TAIL_SKIP=0 issues the MMAs over the zero-filled half of a tap's last K block too
   qasr_stats stats{};
 
   std::map<std::string, std::vector<float>> staged;  // host copies until finalize
@@ -101,13 +112,17 @@ struct qasr_handle {
 
   // workspace (grow-only)
   int stem_group = kStemGroupDefault;
-  long long cap_group = 0, cap_tokens = 0, cap_chunks = 0, cap_windows = 0, cap_batch = 0, cap_mel_frames = 0;
+  long long cap_batch = 0, cap_mel_frames = 0;
   long long cap_io_in = 0, cap_io_out = 0;
-  DevBuf planes1, planes2, flat3, x, xn, qkv, attn, hbuf, mel_scratch, io_in, io_out;
-  DevBuf d_chunks, d_rowmap, d_windows, d_soffs, d_foffs, d_boffs, d_uttmax;
+  Lane lanes[2];
+  bool two_lanes = false;           // QASR_LANES=2 splits large batches over two lanes / two streams (measured: no gain)
+  long long lane_min_chunks = 256;  // batches with fewer 100-frame chunks are not split
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  DevBuf mel_scratch, io_in, io_out;
+  DevBuf d_soffs, d_foffs, d_boffs, d_uttmax;
   DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src;
   long long dbg_tokens = 0;
-  CUtensorMap tm_planes1, tm_planes2, tm_flat3, tm_xn, tm_attn, tm_h, tm_p1, tm_qkv;
   // per-category CUDA-event profiling (qasr_set_profile)
   bool profile = false;
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
@@ -327,57 +342,63 @@ int build_weight_maps(qasr_handle* h) {
   return QASR_OK;
 }
 
-// Grow the workspace so that a call with `tokens`, `chunks`, `windows`, `batch` fits.
-int ensure_workspace(qasr_handle* h, long long tokens, long long chunks, long long windows, long long batch) {
-  const qasr_config& c = h->cfg;
-  const int D = c.d_model, F = c.encoder_ffn_dim;
+// Grow the per-batch tables (mel offsets / per-utterance maxima).
+int ensure_batch_tables(qasr_handle* h, long long batch) {
   int rc;
-  std::string e;
-  const long long group = chunks < h->stem_group ? chunks : h->stem_group;
-  if (group > h->cap_group) {
-    const long long G = group;
-    const size_t p1 = static_cast<size_t>(4) * G * 33 * 26 * kStemC * 2;
-    const size_t p2 = static_cast<size_t>(4) * G * 17 * 14 * kStemC * 2;
-    dev_free(h, h->planes1);
-    dev_free(h, h->planes2);
-    if ((rc = dev_alloc(h, h->planes1, p1, true))) return rc;  // zero borders are never written afterwards
-    if ((rc = dev_alloc(h, h->planes2, p2, true))) return rc;
-    if ((rc = dev_alloc(h, h->flat3, static_cast<size_t>(G) * 13 * 16 * kStemC * 2, true))) return rc;
-    if (!make_tmap_conv_act(&h->tm_planes1, h->planes1.p, kStemC, 26, G * 33, 25, 5, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_conv_act(&h->tm_planes2, h->planes2.p, kStemC, 14, G * 17, 13, 9, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&h->tm_flat3, h->flat3.p, G * 13, 16 * kStemC, 16 * kStemC, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
-    h->cap_group = G;
-  }
-  if (tokens > h->cap_tokens) {
-    const long long n = tokens;
-    const int wide = F > D ? F : D;
-    if ((rc = dev_alloc(h, h->x, static_cast<size_t>(n) * D * 4, false))) return rc;
-    if ((rc = dev_alloc(h, h->xn, static_cast<size_t>(n) * D * 2, true))) return rc;
-    if ((rc = dev_alloc(h, h->qkv, static_cast<size_t>(n) * 3 * D * 2, true))) return rc;  // zeroed: attention tiles over-read finite rows
-    if ((rc = dev_alloc(h, h->attn, static_cast<size_t>(n) * D * 2, true))) return rc;
-    if ((rc = dev_alloc(h, h->hbuf, static_cast<size_t>(n) * wide * 2, true))) return rc;
-    if (!make_tmap_rows(&h->tm_xn, h->xn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&h->tm_attn, h->attn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&h->tm_h, h->hbuf.p, n, F, F, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&h->tm_p1, h->hbuf.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
-    if (!make_tmap_rows(&h->tm_qkv, h->qkv.p, n, 3 * D, 3 * D, 128, &e)) return fail(h, QASR_ERR_CUDA, e);
-    h->cap_tokens = n;
-  }
-  if (chunks > h->cap_chunks) {
-    if ((rc = dev_alloc(h, h->d_chunks, static_cast<size_t>(chunks) * sizeof(ChunkDesc), false))) return rc;
-    if ((rc = dev_alloc(h, h->d_rowmap, static_cast<size_t>(chunks) * kTokensPerChunk * sizeof(int), false))) return rc;
-    h->cap_chunks = chunks;
-  }
-  if (windows > h->cap_windows) {
-    if ((rc = dev_alloc(h, h->d_windows, static_cast<size_t>(windows) * sizeof(WindowDesc), false))) return rc;
-    h->cap_windows = windows;
-  }
   if (batch > h->cap_batch) {
     if ((rc = dev_alloc(h, h->d_soffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
     if ((rc = dev_alloc(h, h->d_foffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
     if ((rc = dev_alloc(h, h->d_boffs, static_cast<size_t>(batch + 1) * 4, false))) return rc;
     if ((rc = dev_alloc(h, h->d_uttmax, static_cast<size_t>(batch) * 4, false))) return rc;
     h->cap_batch = batch;
+  }
+  return QASR_OK;
+}
+
+// Grow one lane's workspace so that a share with `tokens`, `chunks`, `windows` fits.
+int ensure_workspace(qasr_handle* h, Lane& ln, long long tokens, long long chunks, long long windows) {
+  const qasr_config& c = h->cfg;
+  const int D = c.d_model, F = c.encoder_ffn_dim;
+  int rc;
+  std::string e;
+  const long long group = chunks < h->stem_group ? chunks : h->stem_group;
+  if (group > ln.cap_group) {
+    const long long G = group;
+    const size_t p1 = static_cast<size_t>(4) * G * 33 * 26 * kStemC * 2;
+    const size_t p2 = static_cast<size_t>(4) * G * 17 * 14 * kStemC * 2;
+    dev_free(h, ln.planes1);
+    dev_free(h, ln.planes2);
+    if ((rc = dev_alloc(h, ln.planes1, p1, true))) return rc;  // zero borders are never written afterwards
+    if ((rc = dev_alloc(h, ln.planes2, p2, true))) return rc;
+    if ((rc = dev_alloc(h, ln.flat3, static_cast<size_t>(G) * 13 * 16 * kStemC * 2, true))) return rc;
+    if (!make_tmap_conv_act(&ln.tm_planes1, ln.planes1.p, kStemC, 26, G * 33, 25, 5, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_conv_act(&ln.tm_planes2, ln.planes2.p, kStemC, 14, G * 17, 13, 9, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&ln.tm_flat3, ln.flat3.p, G * 13, 16 * kStemC, 16 * kStemC, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    ln.cap_group = G;
+  }
+  if (tokens > ln.cap_tokens) {
+    const long long n = tokens;
+    const int wide = F > D ? F : D;
+    if ((rc = dev_alloc(h, ln.x, static_cast<size_t>(n) * D * 4, false))) return rc;
+    if ((rc = dev_alloc(h, ln.xn, static_cast<size_t>(n) * D * 2, true))) return rc;
+    if ((rc = dev_alloc(h, ln.qkv, static_cast<size_t>(n) * 3 * D * 2, true))) return rc;  // zeroed: attention tiles over-read finite rows
+    if ((rc = dev_alloc(h, ln.attn, static_cast<size_t>(n) * D * 2, true))) return rc;
+    if ((rc = dev_alloc(h, ln.hbuf, static_cast<size_t>(n) * wide * 2, true))) return rc;
+    if (!make_tmap_rows(&ln.tm_xn, ln.xn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&ln.tm_attn, ln.attn.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&ln.tm_h, ln.hbuf.p, n, F, F, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&ln.tm_p1, ln.hbuf.p, n, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&ln.tm_qkv, ln.qkv.p, n, 3 * D, 3 * D, 128, &e)) return fail(h, QASR_ERR_CUDA, e);
+    ln.cap_tokens = n;
+  }
+  if (chunks > ln.cap_chunks) {
+    if ((rc = dev_alloc(h, ln.d_chunks, static_cast<size_t>(chunks) * sizeof(ChunkDesc), false))) return rc;
+    if ((rc = dev_alloc(h, ln.d_rowmap, static_cast<size_t>(chunks) * kTokensPerChunk * sizeof(int), false))) return rc;
+    ln.cap_chunks = chunks;
+  }
+  if (windows > ln.cap_windows) {
+    if ((rc = dev_alloc(h, ln.d_windows, static_cast<size_t>(windows) * sizeof(WindowDesc), false))) return rc;
+    ln.cap_windows = windows;
   }
   return QASR_OK;
 }
@@ -489,7 +510,7 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
     boffs[u + 1] = static_cast<int>(nb);
   }
   int rc;
-  if ((rc = ensure_workspace(h, 0, 0, 0, B))) return rc;
+  if ((rc = ensure_batch_tables(h, B))) return rc;
   const size_t b8 = static_cast<size_t>(B + 1) * 8, b4 = static_cast<size_t>(B + 1) * 4;
   uint8_t* pin = pin_take(h, 2 * b8 + b4);
   if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
@@ -521,12 +542,11 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
   return QASR_OK;
 }
 
-int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
-                int out_dtype, int64_t* token_offsets_out, cudaStream_t st) {
-  if (!h->finalized) return fail(h, QASR_ERR_STATE, "weights not finalised (call qasr_finalize_weights)");
-  if (!mel_dev || !frame_offsets || !emb_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
-  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
-  if (frame_offsets[0] != 0) return fail(h, QASR_ERR_INVALID, "frame_offsets[0] must be 0");
+// mel + ... -> embeddings for the utterances [0, B) described by ABSOLUTE frame offsets (frame_offsets[0] may be > 0:
+// a lane's share starts in the middle of the packed mel buffer), on one lane's workspace and one stream.
+// toffs (B + 1 entries, relative to the share's first token) is filled in.
+int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
+                int out_dtype, long long* toffs, cudaStream_t st) {
   const qasr_config& c = h->cfg;
   const int D = c.d_model, F = c.encoder_ffn_dim, H = c.encoder_attention_heads;
   const int wtok = window_tokens(c);
@@ -535,7 +555,7 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   std::vector<ChunkDesc> chunks;
   std::vector<int> rowmap;
   std::vector<WindowDesc> windows;
-  std::vector<long long> toffs(B + 1, 0);
+  toffs[0] = 0;
   for (int u = 0; u < B; ++u) {
     const long long T = frame_offsets[u + 1] - frame_offsets[u];
     if (T <= 0 || T > 0x7FFFFFF0LL) return fail(h, QASR_ERR_INVALID, "utterance with no mel frames");
@@ -556,29 +576,27 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   const long long n = toffs[B];
   const long long nchunks = static_cast<long long>(chunks.size());
   const long long nwin = static_cast<long long>(windows.size());
-  if (token_offsets_out)
-    for (int u = 0; u <= B; ++u) token_offsets_out[u] = toffs[u];
 
   int rc;
-  if ((rc = ensure_workspace(h, n, nchunks, nwin, B))) return rc;
+  if ((rc = ensure_workspace(h, ln, n, nchunks, nwin))) return rc;
   const size_t bc = chunks.size() * sizeof(ChunkDesc), br = rowmap.size() * sizeof(int), bw = windows.size() * sizeof(WindowDesc);
   uint8_t* pin = pin_take(h, bc + br + bw);
   if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
   memcpy(pin, chunks.data(), bc);
   memcpy(pin + bc, rowmap.data(), br);
   memcpy(pin + bc + br, windows.data(), bw);
-  QCUDA(h, cudaMemcpyAsync(h->d_chunks.p, pin, bc, cudaMemcpyHostToDevice, st));
-  QCUDA(h, cudaMemcpyAsync(h->d_rowmap.p, pin + bc, br, cudaMemcpyHostToDevice, st));
-  QCUDA(h, cudaMemcpyAsync(h->d_windows.p, pin + bc + br, bw, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(ln.d_chunks.p, pin, bc, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(ln.d_rowmap.p, pin + bc, br, cudaMemcpyHostToDevice, st));
+  QCUDA(h, cudaMemcpyAsync(ln.d_windows.p, pin + bc + br, bw, cudaMemcpyHostToDevice, st));
 
-  float* x = static_cast<float*>(h->x.p);
-  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(h->xn.p);
-  __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(h->qkv.p);
-  __nv_bfloat16* attn = static_cast<__nv_bfloat16*>(h->attn.p);
-  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h->hbuf.p);
+  float* x = static_cast<float*>(ln.x.p);
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(ln.xn.p);
+  __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(ln.qkv.p);
+  __nv_bfloat16* attn = static_cast<__nv_bfloat16*>(ln.attn.p);
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(ln.hbuf.p);
 
   // ---- conv stem, in groups of chunks so that the activation planes stay bounded
-  const long long G = h->cap_group;
+  const long long G = ln.cap_group;
   const long long ps1 = G * 33 * 26 * kStemC, ps2 = G * 17 * 14 * kStemC;
   for (long long c0 = 0; c0 < nchunks; c0 += G) {
     const int g = static_cast<int>(nchunks - c0 < G ? nchunks - c0 : G);
@@ -586,49 +604,49 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       ProfScope ps(h, QASR_PROF_CONV1, st, 2.0 * 64 * 50 * kStemC * 9 * g, (4.0 * 128 * 100 + 2.0 * 64 * 50 * kStemC) * g);
       if (h->conv1_fp32)
         conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
-            mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
-            static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+            mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
+            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1);
       else
         conv1_gelu_tc_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1TcThreads, 0, st>>>(
-            mel_dev, static_cast<const ChunkDesc*>(h->d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
-            static_cast<__nv_bfloat16*>(h->planes1.p), ps1);
+            mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
+            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1);
     }
     QCUDA(h, cudaGetLastError());
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
       GemmParams p{};
       p.M = g * 33 * 25; p.N = kStemC; p.K = 9 * kStemC;
-      p.conv_OW = 25; p.conv_OH = 32; p.conv_OHp = 33; p.conv_rows_per_tile = 5; p.a_tx_bytes = 5 * 25 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_OW = 25; p.conv_OH = 32; p.conv_OHp = 33; p.conv_rows_per_tile = 5; p.a_tx_bytes = 5 * 25 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK; p.conv_tail_k16 = h->conv_tail_skip ? (kStemC % kBlockK) / kUmmaK : 0;
       p.conv_chunks = g;
       p.num_m_tiles = (g * 33 + 4) / 5;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
-      p.out = h->planes2.p; p.bias = h->conv2_b;
+      p.out = ln.planes2.p; p.bias = h->conv2_b;
       p.out_Hp = 17; p.out_Wp = 14; p.out_plane_stride = ps2; p.out_C = kStemC;
       ProfScope ps(h, QASR_PROF_CONV2, st, 2.0 * 32 * 25 * kStemC * 9 * kStemC * g, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_PLANES, 2>(h->tm_planes1, h->tm_conv2_w.m2, p, st)));
-      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES, 1>(h->tm_planes1, h->tm_conv2_w.m1, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_PLANES, 2>(ln.tm_planes1, h->tm_conv2_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_PLANES, 1>(ln.tm_planes1, h->tm_conv2_w.m1, p, st)));
     }
     {  // conv3: (g,32,25,480) -> (g,16,13,480), written as conv_out's A operand [(g*13), 16*480]
       GemmParams p{};
       p.M = g * 17 * 13; p.N = kStemC; p.K = 9 * kStemC;
-      p.conv_OW = 13; p.conv_OH = 16; p.conv_OHp = 17; p.conv_rows_per_tile = 9; p.a_tx_bytes = 9 * 13 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK;
+      p.conv_OW = 13; p.conv_OH = 16; p.conv_OHp = 17; p.conv_rows_per_tile = 9; p.a_tx_bytes = 9 * 13 * kBlockK * 2; p.conv_kc_per_tap = (kStemC + kBlockK - 1) / kBlockK; p.conv_tail_k16 = h->conv_tail_skip ? (kStemC % kBlockK) / kUmmaK : 0;
       p.conv_chunks = g;
       p.num_m_tiles = (g * 17 + 8) / 9;
       p.num_k_blocks = 9 * p.conv_kc_per_tap;
-      p.out = h->flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
+      p.out = ln.flat3.p; p.bias = h->conv3_b; p.out_C = kStemC;
       ProfScope ps(h, QASR_PROF_CONV3, st, 2.0 * 16 * 13 * kStemC * 9 * kStemC * g, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_FLAT, 2>(h->tm_planes2, h->tm_conv3_w.m2, p, st)));
-      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT, 1>(h->tm_planes2, h->tm_conv3_w.m1, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<240, kPairStages, A_CONV, EPI_CONV_FLAT, 2>(ln.tm_planes2, h->tm_conv3_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<240, kGemmStages, A_CONV, EPI_CONV_FLAT, 1>(ln.tm_planes2, h->tm_conv3_w.m1, p, st)));
     }
     {  // conv_out + positional embedding + strip padding + pack (encoder.py:277-293)
       GemmParams p = dense_params(g * kTokensPerChunk, D, 16 * kStemC, x, D, nullptr);
-      p.row_map = static_cast<const int*>(h->d_rowmap.p) + c0 * kTokensPerChunk;
+      p.row_map = static_cast<const int*>(ln.d_rowmap.p) + c0 * kTokensPerChunk;
       p.pe = h->pe; p.pe_period = kTokensPerChunk;
       ProfScope ps(h, QASR_PROF_CONV_OUT, st, 2.0 * g * kTokensPerChunk * D * 16 * kStemC, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_CONVOUT_PACK, 2>(h->tm_flat3, h->tm_convout_w.m2, p, st)));
-      else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK, 1>(h->tm_flat3, h->tm_convout_w.m1, p, st)));
+      if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_CONVOUT_PACK, 2>(ln.tm_flat3, h->tm_convout_w.m2, p, st)));
+      else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK, 1>(ln.tm_flat3, h->tm_convout_w.m1, p, st)));
     }
   }
-  if (h->debug) {
+  if (h->debug) {  // debug calls always run on a single lane
     if ((rc = dev_alloc(h, h->dbg_stem, static_cast<size_t>(n) * D * 4, false))) return rc;
     if ((rc = dev_alloc(h, h->dbg_layer0, static_cast<size_t>(n) * D * 4, false))) return rc;
     if ((rc = dev_alloc(h, h->dbg_hidden, static_cast<size_t>(n) * D * 4, false))) return rc;
@@ -644,24 +662,24 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   for (size_t li = 0; li < h->layers.size(); ++li) {
     LayerWeights& L = h->layers[li];
     if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, h->tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, ln.tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
     {
       ProfScope ps(h, QASR_PROF_ATTENTION, st, attn_flops, 8.0 * n * D);
       if (h->attn_tc) {
         const long long items = nwin * H;
         const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
-        window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(h->tm_qkv, static_cast<const WindowDesc*>(h->d_windows.p),
+        window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(ln.tm_qkv, static_cast<const WindowDesc*>(ln.d_windows.p),
                                                                       static_cast<int>(nwin), H, D, attn, scale_log2e);
       } else {
         window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
-            qkv, static_cast<const WindowDesc*>(h->d_windows.p), attn, D, scale_log2e);
+            qkv, static_cast<const WindowDesc*>(ln.d_windows.p), attn, D, scale_log2e);
       }
     }
     QCUDA(h, cudaGetLastError());
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, h->tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, ln.tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
     if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, h->tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, h->tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
+    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, ln.tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, ln.tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
     if (h->debug && li == 0)
       QCUDA(h, cudaMemcpyAsync(h->dbg_layer0.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -669,12 +687,65 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
 
   // ---- projector (encoder.py:319-321)
   if ((rc = layernorm(h, x, h->lnp_g, h->lnp_b, xn, ni, st))) return rc;
-  if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_PROJ, h->tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
+  if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_PROJ, ln.tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
   if (out_dtype == QASR_F32) {
-    if ((rc = dense<EPI_STORE_F32>(h, QASR_PROF_GEMM_PROJ, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+    if ((rc = dense<EPI_STORE_F32>(h, QASR_PROF_GEMM_PROJ, ln.tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
   } else {
-    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_PROJ, h->tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_PROJ, ln.tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
   }
+  return QASR_OK;
+}
+
+long long chunks_of(long long frames) { return (frames + kChunkFrames - 1) / kChunkFrames; }
+
+// The encoder over a whole call: one lane, or two lanes on two streams when the batch is large enough.
+// Utterances are independent (the reference loops over them one at a time, model.py:239), so the split
+// changes no result; it is made at the utterance boundary that balances the 100-frame chunk counts.
+int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
+                int out_dtype, int64_t* token_offsets_out, cudaStream_t st) {
+  if (!h->finalized) return fail(h, QASR_ERR_STATE, "weights not finalised (call qasr_finalize_weights)");
+  if (!mel_dev || !frame_offsets || !emb_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
+  if (frame_offsets[0] != 0) return fail(h, QASR_ERR_INVALID, "frame_offsets[0] must be 0");
+  long long total_chunks = 0;
+  for (int u = 0; u < B; ++u) {
+    if (frame_offsets[u + 1] - frame_offsets[u] <= 0) return fail(h, QASR_ERR_INVALID, "utterance with no mel frames");
+    total_chunks += chunks_of(frame_offsets[u + 1] - frame_offsets[u]);
+  }
+  int split = B;  // utterances [0, split) -> lane 0, [split, B) -> lane 1
+  if (h->two_lanes && !h->debug && B >= 2 && total_chunks >= h->lane_min_chunks) {
+    long long acc = 0, best = -1;
+    for (int u = 0; u + 1 < B; ++u) {
+      acc += chunks_of(frame_offsets[u + 1] - frame_offsets[u]);
+      const long long d = acc * 2 > total_chunks ? acc * 2 - total_chunks : total_chunks - acc * 2;
+      if (best < 0 || d < best) { best = d; split = u + 1; }
+    }
+  }
+  std::vector<long long> toffs(B + 2, 0);
+  int rc;
+  if (split >= B) {
+    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, B, emb_dev, out_dtype, toffs.data(), st))) return rc;
+  } else {
+    // Profiling brackets every launch with events on ONE stream: the lanes then run back to back on `st`.
+    cudaStream_t st1 = h->profile ? st : h->lane_stream;
+    if (!h->profile) {
+      QCUDA(h, cudaEventRecord(h->ev_fork, st));
+      QCUDA(h, cudaStreamWaitEvent(st1, h->ev_fork, 0));
+    }
+    std::vector<long long> t0(split + 1), t1(B - split + 1);
+    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, split, emb_dev, out_dtype, t0.data(), st))) return rc;
+    const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
+    void* emb1 = static_cast<uint8_t*>(emb_dev) + static_cast<size_t>(t0[split]) * h->cfg.output_dim * esz;
+    if ((rc = encode_lane(h, h->lanes[1], mel_dev, frame_offsets + split, B - split, emb1, out_dtype, t1.data(), st1))) return rc;
+    if (!h->profile) {
+      QCUDA(h, cudaEventRecord(h->ev_join, st1));
+      QCUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    }
+    for (int u = 0; u <= split; ++u) toffs[u] = t0[u];
+    for (int u = 1; u <= B - split; ++u) toffs[split + u] = t0[split] + t1[u];
+  }
+  if (token_offsets_out)
+    for (int u = 0; u <= B; ++u) token_offsets_out[u] = toffs[u];
   return QASR_OK;
 }
 
@@ -717,15 +788,21 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, QASR_ERR_CUDA, "cudaSetDevice failed"); }
   if (const char* c1 = getenv("QASR_CONV1_FP32")) h->conv1_fp32 = atoi(c1) != 0;
   if (const char* cp = getenv("QASR_CTA_PAIR")) h->cta_pair = atoi(cp) != 0;
+  if (const char* ts = getenv("QASR_CONV_TAIL_SKIP")) h->conv_tail_skip = atoi(ts) != 0;
   if (const char* at = getenv("QASR_ATTN_TC")) h->attn_tc = atoi(at) != 0;
   if (const char* sg = getenv("QASR_STEM_GROUP")) {
     const int v = atoi(sg);
     if (v > 0) h->stem_group = v;
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
+  if (const char* ls = getenv("QASR_LANES")) h->two_lanes = atoi(ls) >= 2;
+  if (const char* lm = getenv("QASR_LANE_MIN_CHUNKS")) h->lane_min_chunks = atoll(lm);
   if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -750,10 +827,15 @@ void qasr_destroy(qasr_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->weight_allocs) cudaFree(p);
-  DevBuf* bufs[] = {&h->planes1, &h->planes2, &h->flat3, &h->x, &h->xn, &h->qkv, &h->attn, &h->hbuf, &h->mel_scratch,
-                    &h->io_in, &h->io_out, &h->d_chunks, &h->d_rowmap, &h->d_windows, &h->d_soffs, &h->d_foffs,
+  DevBuf* bufs[] = {&h->mel_scratch, &h->io_in, &h->io_out, &h->d_soffs, &h->d_foffs,
                     &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden, &h->d_prompt_src};
   for (DevBuf* b : bufs) dev_free(h, *b);
+  for (Lane& ln : h->lanes)
+    for (DevBuf* b : {&ln.planes1, &ln.planes2, &ln.flat3, &ln.x, &ln.xn, &ln.qkv, &ln.attn, &ln.hbuf, &ln.d_chunks, &ln.d_rowmap, &ln.d_windows})
+      dev_free(h, *b);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   invalidate_graphs(h);
@@ -878,7 +960,8 @@ int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch) {
   const long long chunks = total_frames / kChunkFrames + batch;
   const long long tokens = chunks * kTokensPerChunk;
   const long long windows = tokens / window_tokens(h->cfg) + batch;
-  if ((rc = ensure_workspace(h, tokens, chunks, windows, batch))) return rc;
+  if ((rc = ensure_batch_tables(h, batch))) return rc;
+  if ((rc = ensure_workspace(h, h->lanes[0], tokens, chunks, windows))) return rc;
   if (total_frames > h->cap_mel_frames) {
     if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(total_frames) * kMelBins * 4, false))) return rc;
     h->cap_mel_frames = total_frames;

@@ -161,8 +161,10 @@ def test_stem_grouping_is_transparent(small, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"QASR_CTA_PAIR": "0"}, {"QASR_ATTN_TC": "0"}, {"QASR_CONV1_FP32": "1"},
-                                 {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_GRAPHS": "0"}],
-                         ids=["single_cta_gemm", "mma_sync_attention", "conv1_cuda_cores_fp32_weights", "all_alternative_kernels_eager"])
+                                 {"QASR_CTA_PAIR": "0", "QASR_ATTN_TC": "0", "QASR_GRAPHS": "0"},
+                                 {"QASR_LANES": "2", "QASR_LANE_MIN_CHUNKS": "1"}, {"QASR_CONV_TAIL_SKIP": "0"}],
+                         ids=["single_cta_gemm", "mma_sync_attention", "conv1_cuda_cores_fp32_weights", "all_alternative_kernels_eager",
+                              "two_lanes_two_streams", "conv_tail_zero_mmas_issued"])
 def test_kernel_variants_agree(small, monkeypatch, env):
     """The alternative kernels (cta_group::1 GEMM, mma.sync attention, eager launches) give the same
     embeddings as the default configuration (cta_group::2 GEMM, tcgen05 attention, graph replay)."""
