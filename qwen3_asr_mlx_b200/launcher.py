@@ -101,25 +101,34 @@ def encode_sharded(encode_fn: EncodeFn, n_samples: Sequence[int], output_dim: in
 
 def gather_embeddings(local: torch.Tensor, parts: List[List[int]], costs: Sequence[int], output_dim: int, rank: int,
                       world_size: int, group=None) -> torch.Tensor:
-    """Final gather (all-gather-v on a max-padded buffer) + restore of the original utterance order."""
+    """Final gather (all-gather-v on a max-padded buffer) + restore of the original utterance order.
+
+    The order is restored by ONE row gather (``index_select`` with a host-built row map) instead of a
+    copy per utterance: at config 3 (4096 utterances) the per-utterance loop cost more than the collective."""
     per_rank = [sum(int(costs[i]) for i in p) for p in parts]
     total = sum(per_rank)
+    costs_np = np.asarray([int(c) for c in costs], dtype=np.int64)
+    offsets = np.zeros(len(costs) + 1, dtype=np.int64)
+    np.cumsum(costs_np, out=offsets[1:])
     if world_size == 1:
-        gathered = [local]
+        pad, flat = per_rank[0], local
     else:
         pad = max(per_rank)
-        buf = torch.zeros((pad, output_dim), dtype=local.dtype, device=local.device)
-        buf[: local.shape[0]].copy_(local)
-        out = torch.empty((world_size * pad, output_dim), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, buf, group=group)
-        gathered = [out[r * pad: r * pad + per_rank[r]] for r in range(world_size)]
-    result = torch.empty((total, output_dim), dtype=local.dtype, device=local.device)
-    offsets = np.zeros(len(costs) + 1, dtype=np.int64)
-    np.cumsum(np.asarray(costs, dtype=np.int64), out=offsets[1:])
+        buf = local
+        if local.shape[0] != pad:  # only the short ranks pad; the tail rows are never read back
+            buf = torch.empty((pad, output_dim), dtype=local.dtype, device=local.device)
+            buf[: local.shape[0]].copy_(local)
+        flat = torch.empty((world_size * pad, output_dim), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(flat, buf.contiguous(), group=group)
+    # source row of every utterance's first token inside `flat`
+    start = np.zeros(len(costs), dtype=np.int64)
     for r, p in enumerate(parts):
-        pos = 0
-        for i in p:
-            n = int(costs[i])
-            result[int(offsets[i]): int(offsets[i]) + n].copy_(gathered[r][pos: pos + n])
-            pos += n
-    return result
+        if p:
+            idx = np.asarray(p, dtype=np.int64)
+            pos = np.zeros(len(p), dtype=np.int64)
+            np.cumsum(costs_np[idx][:-1], out=pos[1:])
+            start[idx] = r * pad + pos
+    if world_size == 1 and np.array_equal(start, offsets[:-1]):
+        return flat  # already in original order
+    src = np.repeat(start - offsets[:-1], costs_np) + np.arange(total, dtype=np.int64)
+    return flat.index_select(0, torch.from_numpy(src).to(flat.device, non_blocking=True))
