@@ -134,6 +134,17 @@ int qasr_prepare_inputs(qasr_handle* h, const int32_t* input_ids, int64_t n_ids,
                         int64_t vocab, int32_t hidden, const void* audio_emb_dev, int audio_dtype, int64_t n_audio,
                         int32_t audio_pad_id, void* out_dev, void* stream);
 
+/* Long-audio splitter, the feeder of this path (reference _find_split_points, src/qwen3_asr_mlx/model.py:454-513, called at
+ * model.py:400-403): float32 RMS energy of every frame_samples-long frame (bit-identical to the reference's
+ * np.sqrt(np.mean(frame ** 2)), numpy pairwise summation order included) and, for every multiple of chunk_samples below
+ * n_samples, the first lowest-energy frame within +-search_samples (cut = frame start; the boundary itself when the search
+ * window is degenerate).  audio_dev is a DEVICE pointer; points_out is a HOST array of max_points entries; the call
+ * synchronises `stream`.  energy_out_dev (n_samples / frame_samples floats, device) may be NULL.
+ * Returns QASR_ERR_INVALID when more than max_points cuts are needed (n_points_out then holds the required count). */
+int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_samples, int64_t chunk_samples, int64_t search_samples,
+                           int32_t frame_samples, int64_t* points_out, int32_t max_points, int32_t* n_points_out,
+                           float* energy_out_dev, void* stream);
+
 /* ---- constant tables, as the library builds them (for parity tests) ---- */
 int qasr_mel_filterbank(float* out_128x201);
 int qasr_hann_window(float* out_400);

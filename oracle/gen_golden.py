@@ -79,6 +79,24 @@ def main():
         cases[name + "_args"] = np.array([n, chunk, search, 4200 + i])
         cases[name + "_points"] = np.array(ref_split(x, chunk, search), dtype=np.int64)
     np.savez_compressed(os.path.join(GOLDEN, "split_points_reference.npz"), **cases)
+    # frame energies with the reference's own expression (model.py:489-495) for the device kernel's bit-exact check,
+    # plus the reference's split points on a config-4-style file (noise/tones with near-silent gaps; 120 s, 30 s chunks)
+    # and with a non-default frame size (generic summation path)
+    en = {}
+    for i, (name, (n, chunk, search, frame)) in enumerate({"p": (16000 * 120 + 77, 480000, 80000, 480), "q": (16000 * 40, 160000, 80000, 400),
+                                                          "r": (16000 * 21 + 5, 100000, 30000, 1000), "s": (479, 100, 100, 480),
+                                                          "t": (16000 * 9, 16000, 32000, 480)}.items()):
+        r = np.random.default_rng(5200 + i)
+        x = (0.1 * r.standard_normal(n)).astype(np.float32)
+        pos = 0
+        while pos < n:
+            pos += int(r.uniform(3.0, 6.0) * 16000)
+            x[pos: pos + 8000] *= np.float32(1e-3)
+        nf = n // frame
+        en[name + "_args"] = np.array([n, chunk, search, frame, 5200 + i])
+        en[name + "_energy"] = np.array([np.sqrt(np.mean(x[j * frame: (j + 1) * frame] ** 2)) for j in range(nf)], dtype=np.float32)
+        en[name + "_points"] = np.array(ref_split(x, chunk, search, frame), dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "split_energy_reference.npz"), **en)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

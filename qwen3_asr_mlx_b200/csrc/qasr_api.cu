@@ -18,6 +18,7 @@
 #include "encoder_kernels.cuh"
 #include "gemm_host.cuh"
 #include "mel.cuh"
+#include "split.cuh"
 
 using namespace qasr;
 
@@ -121,7 +122,7 @@ struct qasr_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf mel_scratch, io_in, io_out;
   DevBuf d_soffs, d_foffs, d_boffs, d_uttmax;
-  DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src;
+  DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src, d_energy, d_points;
   long long dbg_tokens = 0;
   // per-category CUDA-event profiling (qasr_set_profile)
   bool profile = false;
@@ -828,7 +829,7 @@ void qasr_destroy(qasr_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->mel_scratch, &h->io_in, &h->io_out, &h->d_soffs, &h->d_foffs,
-                    &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden, &h->d_prompt_src};
+                    &h->d_boffs, &h->d_uttmax, &h->dbg_stem, &h->dbg_layer0, &h->dbg_hidden, &h->d_prompt_src, &h->d_energy, &h->d_points};
   for (DevBuf* b : bufs) dev_free(h, *b);
   for (Lane& ln : h->lanes)
     for (DevBuf* b : {&ln.planes1, &ln.planes2, &ln.flat3, &ln.x, &ln.xn, &ln.qkv, &ln.attn, &ln.hbuf, &ln.d_chunks, &ln.d_rowmap, &ln.d_windows})
@@ -1312,6 +1313,48 @@ int qasr_prepare_inputs(qasr_handle* h, const int32_t* input_ids, int64_t n_ids,
   }
   QCUDA(h, cudaGetLastError());
   h->stats.kernel_launches++;
+  return QASR_OK;
+}
+
+int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_samples, int64_t chunk_samples, int64_t search_samples,
+                           int32_t frame_samples, int64_t* points_out, int32_t max_points, int32_t* n_points_out,
+                           float* energy_out_dev, void* stream) {
+  if (!h || !audio_dev || n_samples < 0 || chunk_samples <= 0 || search_samples < 0 || frame_samples <= 0 || !n_points_out ||
+      (max_points > 0 && !points_out) || max_points < 0)
+    return fail(h, QASR_ERR_INVALID, "qasr_find_split_points: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  *n_points_out = 0;
+  const long long n_frames = n_samples / frame_samples;
+  if (n_frames == 0) return QASR_OK;  // model.py:486-487
+  const long long n_bound = (n_samples - 1) / chunk_samples;  // multiples of chunk_samples strictly below n_samples
+  *n_points_out = static_cast<int32_t>(n_bound);
+  if (n_bound > max_points) return fail(h, QASR_ERR_INVALID, "qasr_find_split_points: points_out too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* energy = energy_out_dev;
+  if (!energy) {
+    if ((rc = dev_alloc(h, h->d_energy, static_cast<size_t>(n_frames) * 4, false))) return rc;
+    energy = static_cast<float*>(h->d_energy.p);
+  }
+  if (frame_samples == 480) {
+    const long long grid = (n_frames + kRmsWarpsPerCta - 1) / kRmsWarpsPerCta;
+    frame_rms480_kernel<<<static_cast<unsigned>(grid), kRmsWarpsPerCta * 32, 0, st>>>(audio_dev, n_frames, energy);
+  } else {
+    frame_rms_generic_kernel<<<static_cast<unsigned>((n_frames + 127) / 128), 128, 0, st>>>(audio_dev, n_frames, frame_samples, energy);
+  }
+  QCUDA(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  if (n_bound == 0) {
+    QCUDA(h, cudaStreamSynchronize(st));
+    return QASR_OK;
+  }
+  if ((rc = dev_alloc(h, h->d_points, static_cast<size_t>(n_bound) * 8, false))) return rc;
+  split_argmin_kernel<<<static_cast<unsigned>(n_bound), 32, 0, st>>>(energy, n_frames, n_samples, chunk_samples, search_samples,
+                                                                     frame_samples, static_cast<long long*>(h->d_points.p));
+  QCUDA(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  QCUDA(h, cudaMemcpyAsync(points_out, h->d_points.p, static_cast<size_t>(n_bound) * 8, cudaMemcpyDeviceToHost, st));
+  QCUDA(h, cudaStreamSynchronize(st));
   return QASR_OK;
 }
 

@@ -205,6 +205,31 @@ class AudioEncoder:
                                         ctypes.c_void_p(out.data_ptr()), cdt, runtime.i64_ptr(toffs), h.stream_ptr()))
         return DeviceArray(out), toffs
 
+    def find_split_points(self, audio: torch.Tensor, chunk_samples: int, search_samples: int, frame_samples: int = 480,
+                          return_energy: bool = False):
+        """Cut positions for long audio on the device (reference ``_find_split_points``, model.py:454-513):
+        per-frame float32 RMS energy (bit-identical to the reference's numpy expression) and the first
+        lowest-energy frame within +-``search_samples`` of every multiple of ``chunk_samples``.
+        ``audio`` is a 1-D float32 CUDA tensor; returns a list of ints (and the energies if asked)."""
+        h = self._handle
+        if not isinstance(audio, torch.Tensor) or not audio.is_cuda or audio.dtype != torch.float32 or audio.ndim != 1 or not audio.is_contiguous():
+            raise ValueError("audio must be a contiguous 1-D float32 CUDA tensor")
+        if chunk_samples <= 0 or search_samples < 0 or frame_samples <= 0:
+            raise ValueError("chunk_samples and frame_samples must be positive")
+        n = int(audio.shape[0])
+        if n // frame_samples == 0:  # no whole frame: the reference returns [] (model.py:486-487)
+            return ([], torch.empty(0, dtype=torch.float32, device=audio.device)) if return_energy else []
+        max_points = max(1, (n - 1) // int(chunk_samples))
+        points = np.zeros(max_points, dtype=np.int64)
+        count = ctypes.c_int32(0)
+        energy = torch.empty(n // frame_samples, dtype=torch.float32, device=audio.device) if return_energy else None
+        h.check(h.lib.qasr_find_split_points(h.ptr, ctypes.c_void_p(audio.data_ptr()), n, int(chunk_samples), int(search_samples),
+                                             int(frame_samples), runtime.i64_ptr(points), max_points, ctypes.byref(count),
+                                             ctypes.c_void_p(energy.data_ptr()) if energy is not None and energy.numel() else None,
+                                             h.stream_ptr()))
+        pts = [int(v) for v in points[: count.value]]
+        return (pts, energy) if return_energy else pts
+
     def encode_audio_host(self, audio: np.ndarray, soffs: np.ndarray, out: np.ndarray) -> np.ndarray:
         """Host buffers in and out through ``qasr_encode_audio_host`` (H2D and D2H inside the call)."""
         self._ensure_weights()

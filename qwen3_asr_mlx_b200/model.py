@@ -112,6 +112,30 @@ class Qwen3ASR:
         """mel + encoder for a batch -> (packed embeddings, token_offsets)."""
         return self._encoder.encode_audio_batch([self._as_samples(a) for a in audios])
 
+    def encode_long(self, samples: np.ndarray, chunk_duration: float = 30.0, search_seconds: float = 5.0):
+        """Long-audio path of the reference (model.py:382-447) up to the encoder: split at low-energy
+        boundaries and encode every segment (per-segment mel max, like model.py:418) as ONE varlen batch.
+        Returns ``(packed embeddings, token_offsets, [(start, end) sample span of every segment])``."""
+        import torch
+
+        enc = self._encoder
+        dev = enc._handle.torch_device
+        audio = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float32)).to(dev)
+        cuts = enc.find_split_points(audio, int(chunk_duration * SAMPLE_RATE), int(search_seconds * SAMPLE_RATE))
+        spans, prev = [], 0
+        for sp in cuts + [len(samples)]:  # the reference's loop, model.py:408-413,441: empty slices are skipped, prev always moves
+            if sp > prev:
+                spans.append((prev, int(sp)))
+            prev = int(sp)
+        if any(b - a < 160 for a, b in spans):
+            raise ValueError("a segment shorter than one hop (160 samples) cannot be encoded")
+        lengths = np.asarray([0] + [b - a for a, b in spans], dtype=np.int64)
+        soffs = np.cumsum(lengths)
+        contiguous = all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1)) and spans[0][0] == 0
+        packed = audio[: spans[-1][1]] if contiguous else torch.cat([audio[a:b] for a, b in spans])
+        emb, toffs = enc.encode_packed_audio(packed, soffs)
+        return emb, toffs, spans
+
     # ------------------------------------------------------------------ reference API
     def transcribe(self, audio, language: Optional[str] = None, temperature: float = 0.0, top_p: float = 1.0, top_k: int = 0,
                    repetition_penalty: float = 1.2, max_tokens: Optional[int] = None, repetition_context_size: int = 100,
@@ -125,12 +149,12 @@ class Qwen3ASR:
             duration = len(samples) / SAMPLE_RATE
             lang = self._resolve_language(language)
             if duration > chunk_duration:  # strict '>', as in the reference (model.py:313)
-                cuts = _find_split_points(samples, int(chunk_duration * SAMPLE_RATE), int(5.0 * SAMPLE_RATE))
-                bounds = [0] + cuts + [len(samples)]
-                segments = [samples[a:b] for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+                # one upload; the RMS scan + argmin run on the device and the segments are slices of the same buffer
+                emb, toffs, spans = self.encode_long(samples, chunk_duration)
+                segments = [samples[a:b] for a, b in spans]
             else:
                 segments = [samples]
-            emb, toffs = self._encoder.encode_audio_batch(segments)  # per-segment mel max, like model.py:418
+                emb, toffs = self._encoder.encode_audio_batch(segments)
             if self._decoder_backend is None:
                 raise NotImplementedError(
                     "text generation is outside the B200 audio-encoding path: construct Qwen3ASR with a decoder_backend "

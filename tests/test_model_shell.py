@@ -18,6 +18,24 @@ def test_split_points_match_reference_golden(golden_dir):
         assert _find_split_points(x, chunk, search) == list(g[n + "_points"]), n
 
 
+def test_split_points_and_energies_match_reference_golden_gapped(golden_dir):
+    """Config-4-style inputs (near-silent gaps), non-default frame sizes and chunk < search window."""
+    g = np.load(os.path.join(golden_dir, "split_energy_reference.npz"))
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        n, chunk, search, frame, seed = (int(v) for v in g[name + "_args"])
+        r = np.random.default_rng(seed)
+        x = (0.1 * r.standard_normal(n)).astype(np.float32)
+        pos = 0
+        while pos < n:
+            pos += int(r.uniform(3.0, 6.0) * 16000)
+            x[pos: pos + 8000] *= np.float32(1e-3)
+        assert _find_split_points(x, chunk, search, frame) == list(g[name + "_points"]), name
+        nf = n // frame
+        if nf:
+            e = np.sqrt(np.mean(x[: nf * frame].reshape(nf, frame) ** 2, axis=1)).astype(np.float32)
+            assert np.array_equal(e.view(np.uint32), g[name + "_energy"].view(np.uint32)), name
+
+
 def test_split_points_reference_known_answers():
     sr = 16_000
     assert _find_split_points(np.zeros(sr, dtype=np.float32), sr * 20, 5 * sr) == []
