@@ -97,6 +97,17 @@ def main():
         en[name + "_energy"] = np.array([np.sqrt(np.mean(x[j * frame: (j + 1) * frame] ** 2)) for j in range(nf)], dtype=np.float32)
         en[name + "_points"] = np.array(ref_split(x, chunk, search, frame), dtype=np.int64)
     np.savez_compressed(os.path.join(GOLDEN, "split_energy_reference.npz"), **en)
+    # load_audio (audio.py:173-204) executed verbatim on WAV files the tests rebuild byte-for-byte (tests/helpers.py:make_wav)
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import WAV_CASES, make_wav
+    la = {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, kw in WAV_CASES.items():
+            path = os.path.join(td, name + ".wav")
+            open(path, "wb").write(make_wav(**kw))
+            la[name] = np.asarray(mel_ref.module().load_audio(path), dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLDEN, "load_audio_reference.npz"), **la)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -182,3 +182,21 @@ def test_encode_sharded_single_rank_restores_order():
     assert mine == [0, 1, 2, 3, 4]
     for i in range(5):
         assert (emb[int(offs[i]): int(offs[i + 1])] == float(i)).all()
+
+
+def test_load_audio_matches_reference_golden(tmp_path, golden_dir):
+    """WAV decode + linear-interpolation resample == the reference's load_audio (audio.py:103-204), executed verbatim by
+    oracle/gen_golden.py on the same bytes."""
+    import os
+
+    from helpers import WAV_CASES, make_wav
+    from qwen3_asr_mlx_b200.audio import load_audio
+
+    g = np.load(os.path.join(golden_dir, "load_audio_reference.npz"))
+    assert sorted(g.files) == sorted(WAV_CASES)
+    for name, kw in WAV_CASES.items():
+        path = tmp_path / (name + ".wav")
+        path.write_bytes(make_wav(**kw))
+        got = load_audio(path)
+        assert got.dtype == np.float32 and got.ndim == 1
+        assert np.array_equal(got, g[name]), name
