@@ -8,7 +8,8 @@ Drop-in for that path of gabrimatic/qwen3-asr-mlx: the names exported here are t
 __version__ = "0.1.0"
 
 from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
-from .config import AudioEncoderConfig
+from .config import AudioEncoderConfig, TextDecoderConfig
+from .decoder import KVCache, TextDecoder, load_decoder_weights
 from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
 from ._array import DeviceArray
 from .generate import prepare_inputs
@@ -21,6 +22,10 @@ __all__ = [
     "log_mel_spectrogram",
     "log_mel_spectrogram_batch",
     "AudioEncoderConfig",
+    "TextDecoderConfig",
+    "TextDecoder",
+    "KVCache",
+    "load_decoder_weights",
     "AudioEncoder",
     "SinusoidalPositionEmbedding",
     "load_encoder_weights",

@@ -43,6 +43,14 @@ class QasrStats(Structure):
     _fields_ = [("kernel_launches", c_uint64), ("workspace_bytes", c_uint64), ("weight_bytes", c_uint64)]
 
 
+class QasrDecoderConfig(Structure):
+    _fields_ = [
+        ("hidden_size", c_int32), ("num_hidden_layers", c_int32), ("num_attention_heads", c_int32), ("num_key_value_heads", c_int32),
+        ("head_dim", c_int32), ("intermediate_size", c_int32), ("vocab_size", c_int32), ("rms_norm_eps", c_float), ("rope_theta", c_float),
+    ]
+
+
+QASR_DEVICE_PTR = 0x100
 PROF_CATEGORIES = 13
 
 
@@ -85,6 +93,16 @@ _SIGNATURES = {
     "qasr_profile_name": (c_char_p, [c_int]),
     "qasr_set_debug": (c_int, [c_void_p, c_int]),
     "qasr_debug_read": (c_int, [c_void_p, c_char_p, POINTER(c_float), c_size_t]),
+    # include/qasr_decoder.h
+    "qasr_decoder_default_config": (None, [POINTER(QasrDecoderConfig)]),
+    "qasr_decoder_create": (c_int, [c_int, POINTER(QasrDecoderConfig), POINTER(c_void_p)]),
+    "qasr_decoder_destroy": (None, [c_void_p]),
+    "qasr_decoder_last_error": (c_char_p, [c_void_p]),
+    "qasr_decoder_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
+    "qasr_decoder_finalize": (c_int, [c_void_p]),
+    "qasr_decoder_embed_table": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int)]),
+    "qasr_decoder_prefill": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qasr_decoder_get_stats": (c_int, [c_void_p, POINTER(QasrStats)]),
     "qasr_bench_gemm": (c_int, [c_int, c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
     "qasr_test_gemm": (c_int, [c_int, POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
 }
@@ -122,11 +140,15 @@ def last_error(handle=None) -> str:
     return msg.decode("utf-8", "replace") if msg else ""
 
 
-def check(rc: int, handle=None) -> None:
+def check(rc: int, handle=None, decoder: bool = False) -> None:
     """Map a qasr_status to the exception type the reference raises for the same condition."""
     if rc == QASR_OK:
         return
-    msg = last_error(handle) or f"libqasr error {rc}"
+    if decoder:
+        raw = load().qasr_decoder_last_error(handle)
+        msg = (raw.decode("utf-8", "replace") if raw else "") or f"libqasr error {rc}"
+    else:
+        msg = last_error(handle) or f"libqasr error {rc}"
     if rc == QASR_ERR_INVALID:
         raise ValueError(msg)
     if rc == QASR_ERR_NOMEM:

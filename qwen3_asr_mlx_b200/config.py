@@ -1,8 +1,9 @@
-"""Audio-encoder configuration (mirrors AudioEncoderConfig, reference src/qwen3_asr_mlx/config.py:14-58)."""
+"""Audio-encoder and text-decoder configuration (mirror AudioEncoderConfig / TextDecoderConfig, reference
+src/qwen3_asr_mlx/config.py:14-58, 61-100)."""
 from __future__ import annotations
 
 import json
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Any
 
@@ -50,3 +51,38 @@ class AudioEncoderConfig:
             raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
         d = json.loads((path / "config.json").read_text(encoding="utf-8"))
         return cls.from_dict(d)
+
+
+@dataclass
+class TextDecoderConfig:
+    """Hyper-parameters of the Qwen3 text decoder (reference config.py:61-76); defaults are the 1.7B model.
+    ``mrope_section`` / ``rope_interleaved`` are carried but unused, as in the reference decoder (plain RoPE)."""
+
+    hidden_size: int = 2048
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 8
+    head_dim: int = 128
+    intermediate_size: int = 6144
+    hidden_act: str = "silu"
+    vocab_size: int = 151936
+    max_position_embeddings: int = 65536
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1_000_000.0
+    mrope_section: list = field(default_factory=lambda: [24, 20, 20])
+    rope_interleaved: bool = True
+
+    @classmethod
+    def from_dict(cls, d: dict[str, Any]) -> "TextDecoderConfig":
+        """Top-level keys of config.json, defaults for anything absent (reference config.py:78-100)."""
+        defaults = cls()
+        names = ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads", "head_dim", "intermediate_size",
+                 "hidden_act", "vocab_size", "max_position_embeddings", "rms_norm_eps", "rope_theta", "mrope_section", "rope_interleaved")
+        return cls(**{n: d.get(n, getattr(defaults, n)) for n in names})
+
+    @classmethod
+    def from_pretrained(cls, model_path: str | Path) -> "TextDecoderConfig":
+        path = Path(model_path)
+        if not path.is_dir():
+            raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
+        return cls.from_dict(json.loads((path / "config.json").read_text(encoding="utf-8")))

@@ -38,7 +38,10 @@ enum EpiMode : int {
   EPI_GELU_F32 = 7,      // out_f32[m,n] = gelu(acc + bias)
   // micro-benchmark-only modes (qasr_bench_gemm); never instantiated on the product path
   EPI_DISCARD = 8,       // accumulators are read from TMEM and dropped (main-loop ceiling)
-  EPI_MATH_ONLY = 9      // bias + GELU + pack, nothing written
+  EPI_MATH_ONLY = 9,     // bias + GELU + pack, nothing written
+  // decoder prefill (reference decoder.py:88-99): the weight rows interleave gate and up projections in blocks of 32
+  // (rows 64b..64b+31 = gate[32b..], rows 64b+32..64b+63 = up[32b..]); out_bf16[m, n/2] = silu(gate) * up
+  EPI_SWIGLU_BF16 = 10
 };
 
 constexpr int kBlockM = 128;
@@ -95,7 +98,8 @@ __device__ __forceinline__ int stage_unit(int row, int unit) {
 
 template <int kEpi>
 constexpr bool epi_is_bf16() {
-  return kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT;
+  return kEpi == EPI_STORE_BF16 || kEpi == EPI_GELU_BF16 || kEpi == EPI_CONV_PLANES || kEpi == EPI_CONV_FLAT ||
+         kEpi == EPI_SWIGLU_BF16;
 }
 
 // kDbg = true (micro-benchmark only) makes the MMA-issuing thread account its waiting cycles into the buffer passed
@@ -309,6 +313,41 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccumStride;
+      if constexpr (kEpi == EPI_SWIGLU_BF16) {
+        static_assert(kEpi != EPI_SWIGLU_BF16 || (kChunk == 32 && kNumChunks % 2 == 0), "SwiGLU epilogue needs 64-column pairs");
+#pragma unroll 1
+        for (int pj = half; pj < kNumChunks / 2; pj += 2) {
+          uint32_t ag[32], au[32];
+          ptx::tmem_ld_32x32(taddr + (2 * pj) * 32, ag);
+          ptx::tmem_ld_32x32(taddr + (2 * pj + 1) * 32, au);
+          const int n = n0 + 2 * pj * 32;  // first absolute (interleaved) column of the gate chunk
+          const bool n_ok = n < p.N;
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = silu_fast(__uint_as_float(ag[8 * u + i])) * __uint_as_float(au[8 * u + i]);
+            uint4 q;
+            q.x = ptx::pack_bf16x2(v[0], v[1]);
+            q.y = ptx::pack_bf16x2(v[2], v[3]);
+            q.z = ptx::pack_bf16x2(v[4], v[5]);
+            q.w = ptx::pack_bf16x2(v[6], v[7]);
+            stg[stage_unit<4>(lane, u)] = q;
+          }
+          __syncwarp();
+          const int u = lane & 3, rsub = lane >> 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + rsub;
+            const int d = rowdst[rr];
+            const uint4 q = stg[stage_unit<4>(rr, u)];
+            if (d >= 0 && n_ok)
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + d * row_stride + (n >> 1) + 8 * u) = q;
+          }
+          __syncwarp();
+        }
+      } else {
       uint32_t acc[kChunk];
       if (half < kNumChunks) {
         if constexpr (kChunk == 32) ptx::tmem_ld_32x32(taddr + half * kChunk, acc);
@@ -469,6 +508,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         __syncwarp();  // staging buffer is rewritten by the next chunk
       }
+      }  // generic (non-SwiGLU) epilogues
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -19,6 +19,14 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// SiLU(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x / 2))  (exact identity): 3 ALU ops + 1 MUFU.
+__device__ __forceinline__ float silu_fast(float x) {
+  const float hx = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
+}
+
 // Exact-erf form (libdevice erff), used where the output stays fp32.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -15,9 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # ------------------------------------------------------------------ C ABI
 def header_symbols():
-    text = open(os.path.join(ROOT, "include", "qasr.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(qasr_[a-z0-9_]+)\s*\(", text)))
+    found = set()
+    for header in ("qasr.h", "qasr_decoder.h"):  # every header under include/
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        found |= set(re.findall(r"\b(qasr_[a-z0-9_]+)\s*\(", text))
+    return sorted(found)
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(lib, name), f"libqasr.so does not export {name}"
-    assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table out of sync with include/qasr.h"
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table out of sync with include/*.h"
 
 
 def test_default_config_matches_reference_defaults():

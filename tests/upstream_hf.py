@@ -71,3 +71,38 @@ def build_upstream(cfg, params):
 def upstream_forward(model, mel) -> np.ndarray:
     mel = torch.as_tensor(np.asarray(mel, dtype=np.float32))
     return model(mel, feature_lens=torch.tensor([mel.shape[1]])).last_hidden_state.numpy()
+
+
+def build_upstream_decoder(cfg, params):
+    """The model authors' Qwen3 decoder (transformers models/qwen3/modeling_qwen3.py: GQA, per-head q/k RMSNorm, rotate-half
+    RoPE, SwiGLU, tied lm_head) loaded with our parameter dict; key names match the checkpoint's ``model.*`` names."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+
+    hc = Qwen3Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                     num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                     num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim, hidden_act="silu",
+                     max_position_embeddings=cfg.max_position_embeddings, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                     tie_word_embeddings=True, attention_bias=False, use_sliding_window=False)
+    hc._attn_implementation = "eager"
+    model = Qwen3ForCausalLM(hc).eval().float()
+    sd = {"model." + k: (v.detach().float().cpu() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v, dtype=np.float32)))
+          for k, v in params.items()}
+    sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    result = model.load_state_dict(sd, strict=True)
+    assert not result.missing_keys and not result.unexpected_keys
+    return model
+
+
+@torch.no_grad()
+def upstream_decoder_forward(model, embeddings):
+    emb = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not isinstance(embeddings, torch.Tensor) else embeddings.float().cpu()
+    out = model(inputs_embeds=emb[None], use_cache=True)
+    keys = torch.stack([layer_kv[0][0] for layer_kv in _cache_layers(out.past_key_values)]).numpy()
+    values = torch.stack([layer_kv[1][0] for layer_kv in _cache_layers(out.past_key_values)]).numpy()
+    return out.logits[0].numpy(), keys, values
+
+
+def _cache_layers(cache):
+    if hasattr(cache, "layers"):
+        return [(l.keys, l.values) for l in cache.layers]
+    return list(cache)
