@@ -177,6 +177,55 @@ def emit(line: dict) -> None:
 _REAL_STDOUT = 1
 
 
+def measure_prefill(enc, emb_dev, toffs, steps, encoder_ms, peak):
+    """SURVEY 8f rank 4, reported beside (never inside) the headline metric: the decoder prefill of the SAME batch.  The encoder's
+    embeddings are scattered into the 64 prompts (build_prompt + prepare_inputs) once, then `steps` prefill calls are timed
+    with CUDA events.  Qwen3-ASR-1.7B text decoder, random init (seed 4321), bf16 with fp32 accumulation."""
+    import numpy as np
+    import torch
+
+    from qwen3_asr_mlx_b200 import build_prompt, prepare_inputs
+    from qwen3_asr_mlx_b200 import decoder as dec
+    from qwen3_asr_mlx_b200.config import TextDecoderConfig
+
+    cfg = TextDecoderConfig()
+    d = dec.TextDecoder(cfg, device=torch.cuda.current_device())
+    d.load_weights(dec.random_init(cfg, seed=4321, device=f"cuda:{torch.cuda.current_device()}"))
+    table = d.embed_tokens
+    rows = []
+    for u in range(len(toffs) - 1):
+        n_audio = int(toffs[u + 1] - toffs[u])
+        ids = build_prompt(n_audio, [22574])  # "language" + a one-token language name
+        rows.append(prepare_inputs(emb_dev[int(toffs[u]): int(toffs[u + 1])], ids, table).tensor[0])
+    offs = np.concatenate([[0], np.cumsum([r.shape[0] for r in rows])]).astype(np.int64)
+    x = torch.cat(rows)
+    n = int(offs[-1])
+    for _ in range(2):
+        d.prefill(x, offs)
+    torch.cuda.synchronize()
+    l0 = d.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last, cache = d.prefill(x, offs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    H, Q, KV, I, L = cfg.hidden_size, cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim, cfg.intermediate_size, cfg.num_hidden_layers
+    B = len(offs) - 1
+    flops = 2.0 * n * L * (H * (Q + 2 * KV) + Q * H + 3 * H * I) + 2.0 * B * H * cfg.vocab_size
+    flops += sum(L * 2.0 * 2.0 * (t * (t + 1) / 2) * Q for t in np.diff(offs))
+    audio_s = UTTS_PER_GPU * UTT_SECONDS
+    out = {"workload": f"{B} prompts x {int(offs[1])} rows (audio tokens of the timed batch + 17 prompt tokens), Qwen3-ASR-1.7B text decoder, random init seed 4321",
+           "ms_per_step": ms, "prompt_rows_per_s": n / (ms / 1e3), "audio_s_per_s": audio_s / (ms / 1e3),
+           "algorithmic_tflop_per_step": flops / 1e12, "tflops": flops / (ms / 1e3) / 1e12, "frac_tensor_peak": flops / (ms / 1e3) / 1e12 / peak,
+           "gpu_launches_per_step": (d.stats()["kernel_launches"] - l0) // steps, "kv_cache_bytes": int(cache.keys.numel()) * 4,
+           "finite": bool(torch.isfinite(last.tensor).all().item()),
+           "encoder_plus_prefill_audio_s_per_s": audio_s / ((encoder_ms + ms) / 1e3)}
+    d.close()
+    return out
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -188,6 +237,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the next-stage (decoder prefill) measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -355,6 +405,12 @@ def main():
             a, t, threads = cpu_reference_sample(40)
             cpu_baseline = {"value": a / t, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"40 x {UTT_SECONDS} s utterances of the same workload ({t:.1f} s of CPU work); numpy mel (1 thread, per-frame loop as in the reference) + torch fp32 encoder (all cores)"}
+        next_stage = None
+        if world == 1 and not args.no_prefill:
+            try:
+                next_stage = {"decoder_prefill": measure_prefill(enc, emb_dev, toffs, args.steps, ms_per_step, peak)}
+            except Exception as exc:  # the headline metric must not depend on the next stage
+                next_stage = {"decoder_prefill": {"error": repr(exc)[:300]}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -372,6 +428,7 @@ def main():
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
+            "next_stage": next_stage,
         }
         emit(line)
     if world > 1:
