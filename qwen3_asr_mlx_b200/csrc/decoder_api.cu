@@ -7,12 +7,16 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <map>
 #include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/qasr_decoder.h"
+#include "causal_attention_sm100.cuh"
 #include "decoder_kernels.cuh"
 #include "gemm_host.cuh"
 
@@ -44,6 +48,7 @@ struct qasr_decoder {
   std::string err;
   bool finalized = false;
   qasr_stats stats{};
+  bool attn_tc = true;  // QASR_DEC_ATTN_TC=0 selects the mma.sync causal-attention kernel instead of the tcgen05 one
   __nv_bfloat16* embed = nullptr;
   float* norm_w = nullptr;
   WMaps tm_embed;
@@ -54,7 +59,7 @@ struct qasr_decoder {
   // workspace (grow-only)
   long long cap_tokens = 0, cap_batch = 0, cap_tiles = 0;
   DBuf x, xn, qkv, attn, hbuf, xl, d_pos, d_tiles, d_last;
-  CUtensorMap tm_xn, tm_attn, tm_h, tm_xl;
+  CUtensorMap tm_xn, tm_attn, tm_h, tm_xl, tm_qkv;
   uint8_t* pin = nullptr;
   size_t pin_bytes = 0;
   cudaEvent_t pin_event = nullptr;
@@ -169,7 +174,7 @@ int ensure_ws(qasr_decoder* d, long long n, long long batch, long long tiles) {
     if ((rc = dalloc(d, d->hbuf, static_cast<size_t>(n) * I * 2, true))) return rc;
     if ((rc = dalloc(d, d->d_pos, static_cast<size_t>(n) * 4, false))) return rc;
     if (!make_tmap_rows(&d->tm_xn, d->xn.p, n, H, H, kBlockM, &e) || !make_tmap_rows(&d->tm_attn, d->attn.p, n, Q, Q, kBlockM, &e) ||
-        !make_tmap_rows(&d->tm_h, d->hbuf.p, n, I, I, kBlockM, &e))
+        !make_tmap_rows(&d->tm_h, d->hbuf.p, n, I, I, kBlockM, &e) || !make_tmap_rows(&d->tm_qkv, d->qkv.p, n, Q + 2 * KV, Q + 2 * KV, 128, &e))
       return dfail(d, QASR_ERR_CUDA, e);
     d->cap_tokens = n;
   }
@@ -263,6 +268,9 @@ int qasr_decoder_create(int device, const qasr_decoder_config* cfg, qasr_decoder
         (rc = walloc(d, &L.qn, static_cast<size_t>(cfg->head_dim))) || (rc = walloc(d, &L.kn, static_cast<size_t>(cfg->head_dim))))
       break;
   }
+  if (const char* at = getenv("QASR_DEC_ATTN_TC")) d->attn_tc = atoi(at) != 0;
+  if (!rc && cudaFuncSetAttribute(causal_attention_sm100, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemBytes) != cudaSuccess)
+    rc = dfail(d, QASR_ERR_CUDA, "cudaFuncSetAttribute(causal_attention_sm100) failed");
   if (!rc && cudaEventCreateWithFlags(&d->pin_event, cudaEventDisableTiming) != cudaSuccess) rc = dfail(d, QASR_ERR_CUDA, "event creation failed");
   if (rc) { g_dec_error = d->err; qasr_decoder_destroy(d); return rc; }
   *out = d;
@@ -384,9 +392,12 @@ int qasr_decoder_prefill(qasr_decoder* d, const void* embeds_dev, int embed_dtyp
     const long long a = seq_offsets[u], b = seq_offsets[u + 1];
     if (b <= a) return dfail(d, QASR_ERR_INVALID, "empty prompt in batch");
     for (long long t = a; t < b; ++t) pos[static_cast<size_t>(t)] = static_cast<int>(t - a);
-    for (long long q0 = 0; q0 < b - a; q0 += 64) tiles.push_back(AttnTile{static_cast<int>(a), static_cast<int>(b - a), static_cast<int>(q0)});
+    const int qt = d->attn_tc ? 128 : 64;  // query rows per attention tile
+    for (long long q0 = 0; q0 < b - a; q0 += qt) tiles.push_back(AttnTile{static_cast<int>(a), static_cast<int>(b - a), static_cast<int>(q0)});
     last[u] = static_cast<int>(b - 1);
   }
+  // longest KV loops first: the persistent CTAs of the tcgen05 kernel take items round-robin
+  if (d->attn_tc) std::stable_sort(tiles.begin(), tiles.end(), [](const AttnTile& x, const AttnTile& y) { return x.q0 > y.q0; });
   int rc;
   if ((rc = ensure_ws(d, n, B, static_cast<long long>(tiles.size())))) return rc;
   const size_t bp = pos.size() * 4, bt = tiles.size() * sizeof(AttnTile), bl = last.size() * 4;
@@ -439,8 +450,16 @@ int qasr_decoder_prefill(qasr_decoder* d, const void* embeds_dev, int embed_dtyp
     qknorm_rope_kernel<<<(ni + 7) / 8, 256, 0, st>>>(qkv, static_cast<const int*>(d->d_pos.p), L.qn, L.kn, c.num_attention_heads,
                                                      c.num_key_value_heads, c.rms_norm_eps, log2_theta, kc, vc, ni);
     DCUDA(d, cudaGetLastError());
-    causal_attention_kernel<<<dim3(static_cast<unsigned>(tiles.size()), c.num_attention_heads), kCaThreads, 0, st>>>(
-        qkv, Q + 2 * KV, Q, Q + KV, group, static_cast<const AttnTile*>(d->d_tiles.p), attn, Q, scale_log2e);
+    if (d->attn_tc) {
+      const long long items = static_cast<long long>(tiles.size()) * c.num_attention_heads;
+      const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
+      causal_attention_sm100<<<grid, kCtThreads, kCtSmemBytes, st>>>(d->tm_qkv, static_cast<const AttnTile*>(d->d_tiles.p),
+                                                                    static_cast<int>(tiles.size()), c.num_attention_heads, group, Q, Q + KV,
+                                                                    attn, Q, scale_log2e);
+    } else {
+      causal_attention_kernel<<<dim3(static_cast<unsigned>(tiles.size()), c.num_attention_heads), kCaThreads, 0, st>>>(
+          qkv, Q + 2 * KV, Q, Q + KV, group, static_cast<const AttnTile*>(d->d_tiles.p), attn, Q, scale_log2e);
+    }
     DCUDA(d, cudaGetLastError());
     d->stats.kernel_launches += 2;
     if ((rc = gemm<EPI_RESID_F32>(d, d->tm_attn, L.tm_wo, ni, H, Q, x, H, st))) return rc;

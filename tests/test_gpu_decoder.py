@@ -207,3 +207,29 @@ def test_encoder_to_prefill_pipeline():
         assert rel_err(np.array(last)[u], ref) <= 3e-2  # two bf16 stages chained (encoder 2e-2 budget + decoder)
     enc.close()
     d.close()
+
+
+def test_attention_kernels_agree_and_long_prompts(small, monkeypatch):
+    """The tcgen05 causal attention (default) against the oracle on prompts that need several KV tiles with online-softmax
+    rescaling (1000 rows = 8 tiles), tile-boundary lengths, and against the mma.sync kernel (QASR_DEC_ATTN_TC=0)."""
+    from qwen3_asr_mlx_b200 import decoder as dec
+
+    cfg, params, d = small
+    lens = [1000, 129, 128, 127, 300, 1, 257]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    emb = _emb(21, int(offs[-1]), cfg.hidden_size)
+    last, cache, hid = d.prefill(emb.cuda(), offs, return_hidden=True)
+    hid = np.array(hid)
+    refs = decoder_torch.decoder_prefill_batch(params, cfg, emb, offs)
+    for u, r in enumerate(refs):
+        a, b = int(offs[u]), int(offs[u + 1])
+        assert rel_err(hid[a:b], r["hidden"]) <= EMB_TOL, (u, lens[u])
+        assert rel_err(np.array(last)[u], r["logits"][-1]) <= EMB_TOL, (u, lens[u])
+    monkeypatch.setenv("QASR_DEC_ATTN_TC", "0")
+    alt = dec.TextDecoder(cfg)
+    alt.load_weights(params)
+    hid2 = np.array(alt.prefill(emb.cuda(), offs, return_cache=False, return_hidden=True)[2])
+    assert rel_err(hid2, hid) <= 5e-3  # same math, different accumulation order / bf16 rounding points
+    for u, r in enumerate(refs):
+        assert rel_err(hid2[int(offs[u]): int(offs[u + 1])], r["hidden"]) <= EMB_TOL
+    alt.close()
