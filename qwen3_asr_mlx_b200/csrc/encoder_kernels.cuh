@@ -77,7 +77,7 @@ conv1_gelu_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ c
       float a = br[c];
 #pragma unroll
       for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], patch[t], a);
-      acc[c] = gelu_fast(a);
+      acc[c] = gelu_from_half(a);  // w and bias are pre-scaled by 0.5
     }
     const int h = oh0 + ohl;
     const int plane = 2 * (h & 1) + (ow & 1);
@@ -222,9 +222,9 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int cwarp = warp * 96;
-  // B fragments (weights) and biases stay in registers for the whole CTA
+  // B fragments (weights) stay in registers for the whole CTA.  The bias rides in the contraction: K rows 9 and 10
+  // (zero padding otherwise) hold bf16 hi and lo parts of the bias, the A operand holds 1.0 there.
   uint32_t bw0[12], bw1[12];
-  float bs[3][8];
 #pragma unroll
   for (int grp = 0; grp < 3; ++grp) {
 #pragma unroll
@@ -234,10 +234,14 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
       const uint32_t lo = *reinterpret_cast<const unsigned short*>(wr + 2 * t);
       const uint32_t hi = *reinterpret_cast<const unsigned short*>(wr + 2 * t + 1);
       bw0[grp * 4 + j] = lo | (hi << 16);                                                   // k = 2t, 2t+1
-      bw1[grp * 4 + j] = (t == 0) ? static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(wr + 8)) : 0u;  // k = 8, (9 = 0)
+      const float bv = __ldg(bias + ch);
+      const __nv_bfloat16 b_hi = __float2bfloat16_rn(bv);
+      const __nv_bfloat16 b_lo = __float2bfloat16_rn(bv - __bfloat162float(b_hi));
+      uint32_t k89 = 0u;                                                                    // k = 2t+8, 2t+9
+      if (t == 0) k89 = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(wr + 8)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b_hi)) << 16);
+      else if (t == 1) k89 = static_cast<uint32_t>(__bfloat16_as_ushort(b_lo));
+      bw1[grp * 4 + j] = k89;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bs[grp][i] = __ldg(bias + cwarp + grp * 32 + 8 * t + i);
   }
   __syncthreads();
 
@@ -256,8 +260,9 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
                           h3 = __float2bfloat16_rn(v3), h4 = __float2bfloat16_rn(v4), h5 = __float2bfloat16_rn(v5);
       ahi[0] = ptx::pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
       ahi[1] = ptx::pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
-      ahi[2] = ptx::pack_bf16x2(__bfloat162float(h4), 0.0f);
-      ahi[3] = ptx::pack_bf16x2(__bfloat162float(h5), 0.0f);
+      // k = 2t+8, 2t+9: tap 8 and the constant 1.0 that multiplies bias_hi (t == 0); 1.0 for bias_lo (t == 1)
+      ahi[2] = ptx::pack_bf16x2(t == 1 ? 1.0f : __bfloat162float(h4), t == 0 ? 1.0f : 0.0f);
+      ahi[3] = ptx::pack_bf16x2(t == 1 ? 1.0f : __bfloat162float(h5), t == 0 ? 1.0f : 0.0f);
       alo[0] = ptx::pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
       alo[1] = ptx::pack_bf16x2(v2 - __bfloat162float(h2), v3 - __bfloat162float(h3));
       alo[2] = ptx::pack_bf16x2(v4 - __bfloat162float(h4), 0.0f);
@@ -278,14 +283,14 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
         mma_bf16_16816(acc[j], alo, bw0[grp * 4 + j], bw1[grp * 4 + j]);
       }
       uint4 q_lo, q_hi;
-      q_lo.x = ptx::pack_bf16x2(gelu_fast(acc[0][0] + bs[grp][0]), gelu_fast(acc[0][1] + bs[grp][1]));
-      q_lo.y = ptx::pack_bf16x2(gelu_fast(acc[1][0] + bs[grp][2]), gelu_fast(acc[1][1] + bs[grp][3]));
-      q_lo.z = ptx::pack_bf16x2(gelu_fast(acc[2][0] + bs[grp][4]), gelu_fast(acc[2][1] + bs[grp][5]));
-      q_lo.w = ptx::pack_bf16x2(gelu_fast(acc[3][0] + bs[grp][6]), gelu_fast(acc[3][1] + bs[grp][7]));
-      q_hi.x = ptx::pack_bf16x2(gelu_fast(acc[0][2] + bs[grp][0]), gelu_fast(acc[0][3] + bs[grp][1]));
-      q_hi.y = ptx::pack_bf16x2(gelu_fast(acc[1][2] + bs[grp][2]), gelu_fast(acc[1][3] + bs[grp][3]));
-      q_hi.z = ptx::pack_bf16x2(gelu_fast(acc[2][2] + bs[grp][4]), gelu_fast(acc[2][3] + bs[grp][5]));
-      q_hi.w = ptx::pack_bf16x2(gelu_fast(acc[3][2] + bs[grp][6]), gelu_fast(acc[3][3] + bs[grp][7]));
+      q_lo.x = ptx::pack_bf16x2(gelu_from_half(acc[0][0]), gelu_from_half(acc[0][1]));
+      q_lo.y = ptx::pack_bf16x2(gelu_from_half(acc[1][0]), gelu_from_half(acc[1][1]));
+      q_lo.z = ptx::pack_bf16x2(gelu_from_half(acc[2][0]), gelu_from_half(acc[2][1]));
+      q_lo.w = ptx::pack_bf16x2(gelu_from_half(acc[3][0]), gelu_from_half(acc[3][1]));
+      q_hi.x = ptx::pack_bf16x2(gelu_from_half(acc[0][2]), gelu_from_half(acc[0][3]));
+      q_hi.y = ptx::pack_bf16x2(gelu_from_half(acc[1][2]), gelu_from_half(acc[1][3]));
+      q_hi.z = ptx::pack_bf16x2(gelu_from_half(acc[2][2]), gelu_from_half(acc[2][3]));
+      q_hi.w = ptx::pack_bf16x2(gelu_from_half(acc[3][2]), gelu_from_half(acc[3][3]));
       *reinterpret_cast<uint4*>(d_lo + grp * 32) = q_lo;
       *reinterpret_cast<uint4*>(d_hi + grp * 32) = q_hi;
     }

@@ -29,11 +29,11 @@ namespace qasr {
 enum AMode : int { A_ROWS = 0, A_CONV = 1 };
 enum EpiMode : int {
   EPI_STORE_BF16 = 0,    // out_bf16[m,n] = acc + bias
-  EPI_GELU_BF16 = 1,     // out_bf16[m,n] = gelu(acc + bias)
+  EPI_GELU_BF16 = 1,     // out_bf16[m,n] = gelu(2 (acc + bias)): W and bias are pre-scaled by 0.5 (math.cuh gelu_from_half)
   EPI_RESID_F32 = 2,     // out_f32[m,n] += acc + bias          (residual stream, in place)
   EPI_STORE_F32 = 3,     // out_f32[m,n] = acc + bias
-  EPI_CONV_PLANES = 4,   // gelu(acc+bias) -> bf16, scattered into the next conv's parity planes
-  EPI_CONV_FLAT = 5,     // gelu(acc+bias) -> bf16, [(chunk*OW + ow)*OH + oh][ch]  (conv_out's A operand)
+  EPI_CONV_PLANES = 4,   // gelu(2 (acc+bias)) -> bf16, scattered into the next conv's parity planes (W, bias pre-scaled by 0.5)
+  EPI_CONV_FLAT = 5,     // gelu(2 (acc+bias)) -> bf16, [(chunk*OW + ow)*OH + oh][ch]  (conv_out's A operand)
   EPI_CONVOUT_PACK = 6,  // out_f32[row_map[m], n] = acc + pe[m % period, n]  (PE add + strip padding + pack)
   EPI_GELU_F32 = 7,      // out_f32[m,n] = gelu(acc + bias)
   // micro-benchmark-only modes (qasr_bench_gemm); never instantiated on the product path
@@ -406,7 +406,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if constexpr (kEpi != EPI_STORE_BF16) {
 #pragma unroll
-            for (int i = 0; i < kChunk; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < kChunk; ++i) v[i] = gelu_from_half(v[i]);  // weights and bias carry the 0.5 (see math.cuh)
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {

@@ -19,6 +19,18 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// The same GELU evaluated from h = x / 2: every producer of a GELU input on this path (conv stem, fc1, proj1) has its
+// weights and bias pre-scaled by 0.5 at load time (exact: a power of two), which removes the 0.5 x multiply:
+// u = x p(x^2) = h (2a + 8b h^2 + 32c h^4), GELU = h (1 + tanh u).  6 ALU ops + 1 MUFU.
+__device__ __forceinline__ float gelu_from_half(float h) {
+  const float h2 = fminf(h * h, 9.0f);  // x^2 <= 36
+  float p = fmaf(32.0f * -3.51516781e-04f, h2, 8.0f * 3.70056460e-02f);
+  p = fmaf(p, h2, 2.0f * 7.97507884e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h * p));
+  return fmaf(h, t, h);
+}
+
 // SiLU(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x / 2))  (exact identity): 3 ALU ops + 1 MUFU.
 __device__ __forceinline__ float silu_fast(float x) {
   const float hx = 0.5f * x;

@@ -886,12 +886,18 @@ int qasr_finalize_weights(qasr_handle* h) {
   std::vector<float> w, b, g;
 #define TAKE(name, count, vec) \
   if (!take(h, name, count, vec, miss)) return fail(h, QASR_ERR_STATE, "parameter " + miss)
+  // Every producer of a GELU input carries the GELU's 0.5 in its weights and bias (exact scaling by a power of two;
+  // the kernels evaluate gelu_from_half, math.cuh): conv2d1-3, fc1 of every layer, proj1.
+  auto halve = [](std::vector<float>& v) { for (float& f : v) f *= 0.5f; };
   TAKE("conv2d1.weight", C * 9, w); TAKE("conv2d1.bias", C, b);
+  halve(w); halve(b);
   if ((rc = upload<float>(h, &h->conv1_w, w)) || (rc = upload<float>(h, &h->conv1_b, b))) return rc;
   if ((rc = upload_bf16(h, &h->conv1_w_bf16, w))) return rc;
   TAKE("conv2d2.weight", C * 9 * C, w); TAKE("conv2d2.bias", C, b);
+  halve(w); halve(b);
   if ((rc = upload_bf16(h, &h->conv2_w, w)) || (rc = upload<float>(h, &h->conv2_b, b))) return rc;
   TAKE("conv2d3.weight", C * 9 * C, w); TAKE("conv2d3.bias", C, b);
+  halve(w); halve(b);
   if ((rc = upload_bf16(h, &h->conv3_w, w)) || (rc = upload<float>(h, &h->conv3_b, b))) return rc;
   TAKE("conv_out.weight", D * 16 * C, w);
   {  // reference flat index = channel*16 + freq (encoder.py:277-278); ours = freq*480 + channel
@@ -915,6 +921,7 @@ int qasr_finalize_weights(qasr_handle* h) {
     TAKE(p + "self_attn.out_proj.weight", D * D, w); TAKE(p + "self_attn.out_proj.bias", D, b);
     if ((rc = upload_bf16(h, &L.wo, w)) || (rc = upload<float>(h, &L.bo, b))) return rc;
     TAKE(p + "fc1.weight", F * D, w); TAKE(p + "fc1.bias", F, b);
+    halve(w); halve(b);
     if ((rc = upload_bf16(h, &L.w1, w)) || (rc = upload<float>(h, &L.b1, b))) return rc;
     TAKE(p + "fc2.weight", D * F, w); TAKE(p + "fc2.bias", D, b);
     if ((rc = upload_bf16(h, &L.w2, w)) || (rc = upload<float>(h, &L.b2, b))) return rc;
@@ -926,6 +933,7 @@ int qasr_finalize_weights(qasr_handle* h) {
   TAKE("ln_post.weight", D, g); TAKE("ln_post.bias", D, b);
   if ((rc = upload<float>(h, &h->lnp_g, g)) || (rc = upload<float>(h, &h->lnp_b, b))) return rc;
   TAKE("proj1.weight", D * D, w); TAKE("proj1.bias", D, b);
+  halve(w); halve(b);
   if ((rc = upload_bf16(h, &h->proj1_w, w)) || (rc = upload<float>(h, &h->proj1_b, b))) return rc;
   TAKE("proj2.weight", O * D, w); TAKE("proj2.bias", O, b);
   if ((rc = upload_bf16(h, &h->proj2_w, w)) || (rc = upload<float>(h, &h->proj2_b, b))) return rc;
