@@ -73,10 +73,12 @@ class Qwen3ASR:
     reference signatures.  ``encode`` and ``encode_batch`` expose the hot path directly.
     """
 
-    def __init__(self, config: AudioEncoderConfig, encoder: AudioEncoder, decoder_backend: Optional[DecoderBackend] = None):
+    def __init__(self, config: AudioEncoderConfig, encoder: AudioEncoder, decoder_backend: Optional[DecoderBackend] = None,
+                 decoder=None):
         self._config = config
         self._encoder = encoder
         self._decoder_backend = decoder_backend
+        self._decoder = decoder  # qwen3_asr_mlx_b200.decoder.TextDecoder (prefill on the B200), optional
         self._lock = threading.Lock()
 
     @classmethod
@@ -89,7 +91,14 @@ class Qwen3ASR:
         config = AudioEncoderConfig.from_pretrained(path)
         encoder = AudioEncoder(config, device=kwargs.get("device"))
         load_encoder_weights(encoder, path)
-        return cls(config, encoder, decoder_backend)
+        decoder = None
+        if kwargs.get("load_decoder", False):  # TextDecoder + load_decoder_weights, reference model.py:183-184
+            from .config import TextDecoderConfig
+            from .decoder import TextDecoder, load_decoder_weights
+
+            decoder = TextDecoder(TextDecoderConfig.from_pretrained(path), device=kwargs.get("device"))
+            load_decoder_weights(decoder, path)
+        return cls(config, encoder, decoder_backend, decoder)
 
     # ------------------------------------------------------------------ the hot path
     @staticmethod
@@ -111,6 +120,26 @@ class Qwen3ASR:
     def encode_batch(self, audios: Sequence):
         """mel + encoder for a batch -> (packed embeddings, token_offsets)."""
         return self._encoder.encode_audio_batch([self._as_samples(a) for a in audios])
+
+    def prefill_batch(self, audios: Sequence, language_tokens: Optional[Sequence[int]] = None):
+        """Waveforms -> first-token logits and KV cache for a whole batch, every stage on the device:
+        mel + encoder (model.py:331-335), ``build_prompt`` (model.py:338-339), ONE ``prepare_inputs`` gather for all
+        prompts (generate.py:266) and the decoder prefill (generate.py:269-275).  Needs a ``TextDecoder``.
+        Returns ``(last_logits (B, vocab), KVCache, prompt_offsets (B+1,), audio_token_offsets (B+1,))``."""
+        from .generate import prepare_inputs
+        from .tokenizer import build_prompt
+
+        if self._decoder is None:
+            raise NotImplementedError("no TextDecoder attached: construct Qwen3ASR(..., decoder=TextDecoder) or from_pretrained(load_decoder=True)")
+        emb, toffs = self._encoder.encode_audio_batch([self._as_samples(a) for a in audios])
+        ids: List[int] = []
+        offsets = [0]
+        for u in range(len(toffs) - 1):
+            ids.extend(build_prompt(int(toffs[u + 1] - toffs[u]), language_tokens))
+            offsets.append(len(ids))
+        x = prepare_inputs(emb, ids, self._decoder.embed_tokens)  # pads are filled in order: prompt u gets its own rows
+        last, cache = self._decoder.prefill(x, offsets)
+        return last, cache, np.asarray(offsets, dtype=np.int64), toffs
 
     def encode_long(self, samples: np.ndarray, chunk_duration: float = 30.0, search_seconds: float = 5.0):
         """Long-audio path of the reference (model.py:382-447) up to the encoder: split at low-energy
@@ -184,6 +213,9 @@ class Qwen3ASR:
         if self._encoder is not None:
             self._encoder.close()
         self._encoder = None
+        if getattr(self, "_decoder", None) is not None:
+            self._decoder.close()
+        self._decoder = None
 
     def __enter__(self) -> "Qwen3ASR":
         return self

@@ -233,3 +233,34 @@ def test_attention_kernels_agree_and_long_prompts(small, monkeypatch):
     for u, r in enumerate(refs):
         assert rel_err(hid2[int(offs[u]): int(offs[u + 1])], r["hidden"]) <= EMB_TOL
     alt.close()
+
+
+def test_prefill_batch_shell_matches_manual_pipeline():
+    """Qwen3ASR.prefill_batch (one prepare_inputs gather for all prompts) == the per-utterance pipeline."""
+    import torch
+
+    from qwen3_asr_mlx_b200 import AudioEncoder, AudioEncoderConfig, Qwen3ASR, build_prompt, prepare_inputs, weights
+    from qwen3_asr_mlx_b200 import decoder as dec
+    from qwen3_asr_mlx_b200.config import TextDecoderConfig
+    from helpers import synth
+
+    ecfg = AudioEncoderConfig(d_model=256, encoder_layers=1, encoder_attention_heads=4, encoder_ffn_dim=512, output_dim=256)
+    enc = AudioEncoder(ecfg)
+    enc.load_weights(weights.random_init(ecfg, seed=7))
+    dcfg = TextDecoderConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, intermediate_size=512)
+    d = dec.TextDecoder(dcfg)
+    d.load_weights(dec.random_init(dcfg, seed=5))
+    shell = Qwen3ASR(ecfg, enc, decoder=d)
+    rng = np.random.default_rng(2)
+    xs = [synth(rng, n) for n in (16000 * 2, 16000 * 7 + 99, 8000)]
+    last, cache, poffs, toffs = shell.prefill_batch(xs, [22574])
+    assert last.shape == (3, dcfg.vocab_size) and list(np.diff(poffs)) == [int(t) + 18 for t in np.diff(toffs)]
+    emb, _ = enc.encode_audio_batch(xs)
+    for u in range(3):
+        ids = build_prompt(int(toffs[u + 1] - toffs[u]), [22574])
+        x = prepare_inputs(emb[int(toffs[u]): int(toffs[u + 1])], ids, d.embed_tokens)
+        single = d.prefill(x, return_cache=False)[0]
+        assert np.array_equal(np.array(single)[0], np.array(last)[u])
+    with pytest.raises(NotImplementedError):
+        Qwen3ASR(ecfg, enc).prefill_batch(xs)
+    shell.close()
