@@ -264,3 +264,30 @@ def test_prefill_batch_shell_matches_manual_pipeline():
     with pytest.raises(NotImplementedError):
         Qwen3ASR(ecfg, enc).prefill_batch(xs)
     shell.close()
+
+
+def test_many_prompts_persistent_ctas_deterministic(small):
+    """300 ragged prompts -> several thousand (prompt, 128-query tile, head) items, so every persistent CTA of the tcgen05
+    attention walks many items and KV steps (barrier phases, TMEM reuse, the shared-memory exchange between the two
+    half-row softmax groups).  Results must be identical run to run and match the oracle on sampled prompts."""
+    cfg, params, d = small
+    rng = np.random.default_rng(77)
+    lens = [int(v) for v in rng.integers(1, 600, size=300)]
+    lens[5], lens[17], lens[100] = 128, 256, 384
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    emb = _emb(31, int(offs[-1]), cfg.hidden_size)
+    emb_dev = emb.cuda()
+    first = None
+    for _ in range(6):
+        last, cache, hid = d.prefill(emb_dev, offs, return_hidden=True)
+        got = (np.array(last), np.array(hid), cache.keys.float().cpu().numpy())
+        if first is None:
+            first = got
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(first, got))
+    assert np.isfinite(first[0]).all() and np.isfinite(first[1]).all()
+    for u in (0, 5, 17, 100, 123, 299, int(np.argmax(lens))):
+        a, b = int(offs[u]), int(offs[u + 1])
+        r = decoder_torch.decoder_prefill(params, cfg, emb[a:b])
+        assert rel_err(first[1][a:b], r["hidden"]) <= EMB_TOL, (u, lens[u])
+        assert rel_err(first[0][u], r["logits"][-1]) <= EMB_TOL, (u, lens[u])
