@@ -362,3 +362,43 @@ def test_from_pretrained_local_checkpoint_and_shell(tmp_path, small):
     with Qwen3ASR.from_pretrained(tmp_path) as model:
         with pytest.raises(NotImplementedError):
             model.transcribe(x)
+
+
+def test_full_arch_config4_size_window_independence(full):
+    """BASELINE config 4 size (one 20-minute utterance, 120 000 frames, 15 600 tokens, 150 attention windows): shape and
+    finiteness, and the size-independent property of the block-diagonal attention (encoder.py:297-311): given the same
+    log-mel, the tokens of the first k windows do not depend on anything after them -- bit for bit."""
+    import torch
+
+    from qwen3_asr_mlx_b200 import log_mel_spectrogram
+
+    cfg, params, enc = full
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = 0.1 * torch.randn(1200 * 16000, device="cuda", generator=g)
+    mel = log_mel_spectrogram(x)                       # (128, 120000) on the device, one utterance-wide max (audio.py:275)
+    assert mel.shape == (128, 120000)
+    whole = enc(mel).tensor[0]
+    assert tuple(whole.shape) == (15600, 2048) and bool(torch.isfinite(whole).all())
+    prefix = enc(mel.tensor[:, : 30 * 800].contiguous()).tensor[0]   # 30 windows of 800 frames = 3120 tokens
+    assert tuple(prefix.shape) == (3120, 2048)
+    assert torch.equal(prefix, whole[:3120])
+    middle = enc(mel.tensor[:, 40 * 800: 45 * 800].contiguous()).tensor[0]  # windows restart with the chunk grid: any 800-frame-aligned cut
+    assert torch.equal(middle, whole[40 * 104: 45 * 104])
+
+
+def test_full_arch_config3_style_order_invariance(full):
+    """BASELINE config 3 style (mixed 1-30 s utterances, varlen-packed): an utterance's embeddings do not depend on its
+    position in the batch or on its neighbours -- bit for bit -- and the token counts follow the reference's rule."""
+    cfg, params, enc = full
+    rng = np.random.default_rng(20261018)
+    lengths = [int(n) for n in rng.integers(16000, 480001, size=48)]
+    xs = [synth(np.random.default_rng(100 + i), n) for i, n in enumerate(lengths)]
+    emb, toffs = enc.encode_audio_batch(xs)
+    e = np.array(emb)
+    assert list(np.diff(toffs)) == [enc.num_tokens(n // 160) for n in lengths]
+    perm = rng.permutation(len(xs))
+    emb2, toffs2 = enc.encode_audio_batch([xs[i] for i in perm])
+    e2 = np.array(emb2)
+    for pos, i in enumerate(perm):
+        assert np.array_equal(e2[int(toffs2[pos]): int(toffs2[pos + 1])], e[int(toffs[i]): int(toffs[i + 1])]), i
+    assert np.isfinite(e).all()
