@@ -291,3 +291,14 @@ def test_many_prompts_persistent_ctas_deterministic(small):
         r = decoder_torch.decoder_prefill(params, cfg, emb[a:b])
         assert rel_err(first[1][a:b], r["hidden"]) <= EMB_TOL, (u, lens[u])
         assert rel_err(first[0][u], r["logits"][-1]) <= EMB_TOL, (u, lens[u])
+
+
+def test_very_long_prompt(small):
+    """A 5 000-row prompt (the prompt of a ~6.4-minute single-pass utterance): 40 query tiles, up to 40 KV steps per item."""
+    cfg, params, d = small
+    emb = _emb(41, 5000, cfg.hidden_size)
+    last, cache, hid = d.prefill(emb.cuda(), return_hidden=True)
+    r = decoder_torch.decoder_prefill(params, cfg, emb)
+    assert rel_err(np.array(hid), r["hidden"]) <= EMB_TOL
+    assert rel_err(np.array(last)[0], r["logits"][-1]) <= EMB_TOL
+    assert rel_err(cache.layer(1)[0][0].float().cpu().numpy(), r["keys"][1]) <= EMB_TOL
