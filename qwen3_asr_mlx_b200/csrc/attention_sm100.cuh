@@ -13,7 +13,7 @@
 //                 [128,184) -> ... -> tcgen05.ld O, scale by 1/sum, bf16, swizzled-smem transpose,
 //                 16-byte coalesced stores.  Two groups keep two warps per scheduler busy (the
 //                 single-group version was bound by instruction latency: ncu 4.3 cycles / issue).
-// The MMA thread polls (try_wait) its two kinds of pending work, S = QK^T of the next item and
+// The MMA thread polls (test_wait: never suspends) its two kinds of pending work, S = QK^T of the next item and
 // O = PV of the oldest item, so neither can block the other.
 // The O(n^2) additive mask of the reference never exists: keys beyond the window length get
 // probability exactly 0.  Rows / keys of the 128-token tiles that lie beyond the window are
@@ -105,7 +105,7 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
         // S = Q K^T of item next_qk: needs its smem stage and a drained TMEM slot (at most 2 items ahead of PV)
         if (next_qk < n_mine && next_qk < next_pv + 2) {
           const int j = next_qk, st = j % kAtStages, slot = j & 1;
-          if (ptx::mbar_try_wait(&full[st], (j / kAtStages) & 1) && ptx::mbar_try_wait(&tfree[slot], ((j >> 1) & 1) ^ 1)) {
+          if (ptx::mbar_test_wait(&full[st], (j / kAtStages) & 1) && ptx::mbar_test_wait(&tfree[slot], ((j >> 1) & 1) ^ 1)) {
             ptx::tc_fence_after();
             const uint8_t* sb = stage_base + st * kAtStageBytes;
             const uint64_t qd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sb));
@@ -121,7 +121,7 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
         // O = P V of item next_pv: needs the probabilities written by its softmax group
         if (next_pv < next_qk) {
           const int j = next_pv, st = j % kAtStages, slot = j & 1;
-          if (ptx::mbar_try_wait(&p_ready[slot], (j >> 1) & 1)) {
+          if (ptx::mbar_test_wait(&p_ready[slot], (j >> 1) & 1)) {
             ptx::tc_fence_after();
             const int item = blockIdx.x + j * gridDim.x;
             const int len = windows[item / num_heads].len;

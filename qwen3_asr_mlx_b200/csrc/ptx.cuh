@@ -72,6 +72,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe.  try_wait may suspend the thread for a system-dependent time when the phase is not complete;
+// a thread that polls SEVERAL barriers (the attention MMA issuer) must not sleep on one while another completes.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
 #ifndef QASR_MBAR_SPIN_LIMIT
 #define QASR_MBAR_SPIN_LIMIT (1u << 26)
