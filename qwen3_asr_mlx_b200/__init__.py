@@ -8,7 +8,7 @@ Drop-in for that path of gabrimatic/qwen3-asr-mlx: the names exported here are t
 __version__ = "0.1.0"
 
 from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
-from .config import AudioEncoderConfig, TextDecoderConfig
+from .config import AudioEncoderConfig, ModelConfig, TextDecoderConfig
 from .decoder import KVCache, TextDecoder, load_decoder_weights
 from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
 from ._array import DeviceArray
@@ -23,6 +23,7 @@ __all__ = [
     "log_mel_spectrogram_batch",
     "AudioEncoderConfig",
     "TextDecoderConfig",
+    "ModelConfig",
     "TextDecoder",
     "KVCache",
     "load_decoder_weights",

@@ -86,3 +86,28 @@ class TextDecoderConfig:
         if not path.is_dir():
             raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
         return cls.from_dict(json.loads((path / "config.json").read_text(encoding="utf-8")))
+
+
+@dataclass
+class ModelConfig:
+    """Top-level Qwen3-ASR configuration (reference config.py:103-150): both sub-configs plus the audio special-token ids."""
+
+    audio_encoder: AudioEncoderConfig = field(default_factory=AudioEncoderConfig)
+    text_decoder: TextDecoderConfig = field(default_factory=TextDecoderConfig)
+    audio_token_id: int = 151676
+    audio_start_token_id: int = 151669
+    audio_end_token_id: int = 151670
+
+    @classmethod
+    def from_dict(cls, d: dict[str, Any]) -> "ModelConfig":
+        return cls(audio_encoder=AudioEncoderConfig.from_dict(d), text_decoder=TextDecoderConfig.from_dict(d),
+                   audio_token_id=d.get("audio_token_id", 151676), audio_start_token_id=d.get("audio_start_token_id", 151669),
+                   audio_end_token_id=d.get("audio_end_token_id", 151670))
+
+    @classmethod
+    def from_pretrained(cls, model_path: str | Path) -> "ModelConfig":
+        """``config.json`` of a local model directory (the reference also accepts a hub id; there is no network here)."""
+        path = Path(model_path)
+        if not path.is_dir():
+            raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
+        return cls.from_dict(json.loads((path / "config.json").read_text(encoding="utf-8")))

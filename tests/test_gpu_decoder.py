@@ -302,3 +302,15 @@ def test_very_long_prompt(small):
     assert rel_err(np.array(hid), r["hidden"]) <= EMB_TOL
     assert rel_err(np.array(last)[0], r["logits"][-1]) <= EMB_TOL
     assert rel_err(cache.layer(1)[0][0].float().cpu().numpy(), r["keys"][1]) <= EMB_TOL
+
+
+def test_prefix_consistency_like_cached_decode(small):
+    """Reference tests/test_decoder.py::test_cached_decode_matches_full_context restated for the prefill: the logits at
+    position t of a full-context pass equal the last-position logits of a prefill over the first t + 1 tokens (atol 1e-3
+    there; causal masking makes them the same computation here)."""
+    cfg, params, d = small
+    emb = _emb(51, 300, cfg.hidden_size).cuda()
+    full = np.array(d.prefill(emb, return_cache=False, all_logits=True)[2])
+    for t in (0, 3, 63, 64, 127, 128, 200, 299):
+        last = np.array(d.prefill(emb[: t + 1], return_cache=False)[0])[0]
+        assert np.allclose(last, full[t], atol=1e-3), t
