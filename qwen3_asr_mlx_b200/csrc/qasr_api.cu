@@ -451,7 +451,9 @@ size_t pin_bytes_for(long long batch, long long chunks, long long windows) {
 
 template <int VPL>
 void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
-  layernorm_bf16_kernel<VPL><<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, y, rows, 1e-5f);
+  // 4 warps per CTA (8 K registers): small enough to co-reside with a persistent GEMM CTA of the other lane
+  static const int ln_threads = getenv("QASR_LN_THREADS") ? atoi(getenv("QASR_LN_THREADS")) : 256;
+  layernorm_bf16_kernel<VPL><<<(rows + ln_threads / 32 - 1) / (ln_threads / 32), ln_threads, 0, st>>>(x, g, b, y, rows, 1e-5f);
 }
 int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
   ProfScope ps(h, QASR_PROF_LAYERNORM, st, 0.0, 6.0 * rows * h->cfg.d_model);
