@@ -195,9 +195,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // channels of a pixel (one 16-byte store).
 constexpr int kConv1TcWarps = 5;
 constexpr int kConv1TcThreads = kConv1TcWarps * 32;
+#ifndef QASR_CONV1_MIN_CTAS
+#define QASR_CONV1_MIN_CTAS 4  // 96 registers, 20 warps per SM: 1.87 ms vs 2.11 ms at 3 (the kernel is latency-bound)
+#endif
+constexpr int kConv1TcMinCtas = QASR_CONV1_MIN_CTAS;
 
 template <int C>
-__global__ void __launch_bounds__(kConv1TcThreads, 3)
+__global__ void __launch_bounds__(kConv1TcThreads, kConv1TcMinCtas)
 conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ chunks, int chunk0,
                      const __nv_bfloat16* __restrict__ w /*[C][9] bf16*/, const float* __restrict__ bias /*[C]*/,
                      __nv_bfloat16* __restrict__ planes, long long plane_stride) {
