@@ -369,7 +369,7 @@ def main():
 
     if rank == 0:
         # ------------------------------------------------------------ roofline of the dominant kernel
-        # dominant kernel: gemm_bf16_sm100<256,4,A_ROWS,*> (all nn.Linear call sites), timed live per launch
+        # dominant kernel: gemm_bf16_sm100<256,6,A_ROWS,*,2> (CTA-pair, cta_group::2) (all nn.Linear call sites), timed live per launch
         dense = ["gemm_qkv", "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_projector", "conv_out_gemm"]
         d_ms = sum(prof[k]["ms"] for k in dense)
         d_fl = sum(prof[k]["flops"] for k in dense)
@@ -400,7 +400,7 @@ def main():
                 ent["ncu_dram_bytes_per_launch"] = traffic_by_kernel[k]
             kernels[k] = ent
         roofline = {
-            "kernel": "gemm_bf16_sm100<256,4,A_ROWS,*> (tcgen05 dense GEMM: qkv/out_proj/fc1/fc2/projector/conv_out)",
+            "kernel": "gemm_bf16_sm100<256,6,A_ROWS,*,2> (CTA-pair, cta_group::2) (tcgen05 dense GEMM: qkv/out_proj/fc1/fc2/projector/conv_out)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
             "avg_launch_ms": d_ms / max(d_n, 1), "launches": d_n, "share_of_step": d_ms / total_ms,
