@@ -96,6 +96,10 @@ __device__ __forceinline__ unsigned float_to_ordered(float f) {
 __device__ __forceinline__ float ordered_to_float(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
+// NaN-propagating maximum (numpy semantics); the canonical positive quiet NaN orders above +inf in float_to_ordered,
+// so the per-utterance atomicMax keeps it.
+#define kMelNaN __int_as_float(0x7FC00000)
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? kMelNaN : fmaxf(a, b); }
 // np.pad(mode="reflect") index map (period 2(N-1)); valid for any integer i when N >= 2.
 __device__ __forceinline__ long long reflect_index(long long i, long long n) {
   const long long period = 2 * (n - 1);
@@ -224,20 +228,22 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
       const float* w = s.fb_weight + m * kMelMaxTaps;
       float acc = 0.0f;
       for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], s.P[st + j][f], acc);
-      // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here
-      const float v = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+      // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here.
+      // A non-finite sample makes its frames NaN in the reference (np.maximum / .max() propagate NaN, audio.py:274-275)
+      // and, through the utterance-wide max, the whole utterance: NaN is carried, not dropped by fmaxf.
+      const float v = (acc != acc) ? kMelNaN : __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
       out[static_cast<long long>(m) * T + t0 + f] = v;
-      lmax = fmaxf(lmax, v);
+      lmax = nan_max(lmax, v);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  for (int o = 16; o > 0; o >>= 1) lmax = nan_max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if ((tid & 31) == 0) s.red[tid >> 5] = lmax;
   __syncthreads();
   if (tid == 0) {
     float m = s.red[0];
 #pragma unroll
-    for (int i = 1; i < (kMelThreads + 31) / 32; ++i) m = fmaxf(m, s.red[i]);
+    for (int i = 1; i < (kMelThreads + 31) / 32; ++i) m = nan_max(m, s.red[i]);
     atomicMax(utt_max + u, float_to_ordered(m));
   }
 }
@@ -265,10 +271,14 @@ mel_normalize_kernel(float* __restrict__ mel, const long long* __restrict__ fram
       thr = ordered_to_float(__ldg(utt_max + u)) - 8.0f;
     }
     float4 v = p[e];
-    v.x = (fmaxf(v.x, thr) + 4.0f) * 0.25f;
-    v.y = (fmaxf(v.y, thr) + 4.0f) * 0.25f;
-    v.z = (fmaxf(v.z, thr) + 4.0f) * 0.25f;
-    v.w = (fmaxf(v.w, thr) + 4.0f) * 0.25f;
+    if (thr != thr) {  // a NaN anywhere in the utterance: np.maximum(log_spec, nan) is NaN everywhere (audio.py:275)
+      v = make_float4(thr, thr, thr, thr);
+    } else {
+      v.x = (fmaxf(v.x, thr) + 4.0f) * 0.25f;
+      v.y = (fmaxf(v.y, thr) + 4.0f) * 0.25f;
+      v.z = (fmaxf(v.z, thr) + 4.0f) * 0.25f;
+      v.w = (fmaxf(v.w, thr) + 4.0f) * 0.25f;
+    }
     p[e] = v;
   }
 }

@@ -115,3 +115,18 @@ def test_config4_twenty_minute_utterance(audio_mod):
     got = np.array(audio_mod.log_mel_spectrogram(x))
     assert got.shape == (128, 120000)
     assert np.abs(got - mel_np.log_mel_spectrogram_fast(x)).max() <= MEL_TOL
+
+
+def test_non_finite_samples_poison_the_utterance_like_the_reference(audio_mod):
+    """A NaN / Inf sample makes the reference's log-mel NaN for the WHOLE utterance (np.maximum and .max() propagate NaN,
+    audio.py:274-275; checked against the reference run verbatim) -- and only for that utterance of a batch."""
+    rng = np.random.default_rng(0)
+    clean = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+    for bad in (np.nan, np.inf, -np.inf):
+        x = clean.copy()
+        x[5000] = bad
+        mel, foffs = audio_mod.log_mel_spectrogram_batch([clean, x, clean])
+        m = np.array(mel).reshape(-1)
+        blocks = [m[128 * int(foffs[u]): 128 * int(foffs[u + 1])] for u in range(3)]
+        assert np.isnan(blocks[1]).all()
+        assert np.isfinite(blocks[0]).all() and np.array_equal(blocks[0], blocks[2])
