@@ -99,6 +99,20 @@ def encode_sharded(encode_fn: EncodeFn, n_samples: Sequence[int], output_dim: in
     return gather_embeddings(local, parts, costs, output_dim, rank, world_size, group), global_offsets, mine
 
 
+def gather_start_rows(parts: List[List[int]], costs: np.ndarray, pad: int) -> np.ndarray:
+    """Row of every utterance's first token inside the all-gathered buffer (rank r's share starts at ``r * pad`` and holds
+    its utterances back to back in the order of ``parts[r]``)."""
+    costs = np.asarray(costs, dtype=np.int64)
+    start = np.zeros(len(costs), dtype=np.int64)
+    for r, p in enumerate(parts):
+        if p:
+            idx = np.asarray(p, dtype=np.int64)
+            pos = np.zeros(len(p), dtype=np.int64)
+            np.cumsum(costs[idx][:-1], out=pos[1:])
+            start[idx] = r * pad + pos
+    return start
+
+
 def gather_embeddings(local: torch.Tensor, parts: List[List[int]], costs: Sequence[int], output_dim: int, rank: int,
                       world_size: int, group=None) -> torch.Tensor:
     """Final gather (all-gather-v on a max-padded buffer) + restore of the original utterance order.
@@ -120,14 +134,7 @@ def gather_embeddings(local: torch.Tensor, parts: List[List[int]], costs: Sequen
             buf[: local.shape[0]].copy_(local)
         flat = torch.empty((world_size * pad, output_dim), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(flat, buf.contiguous(), group=group)
-    # source row of every utterance's first token inside `flat`
-    start = np.zeros(len(costs), dtype=np.int64)
-    for r, p in enumerate(parts):
-        if p:
-            idx = np.asarray(p, dtype=np.int64)
-            pos = np.zeros(len(p), dtype=np.int64)
-            np.cumsum(costs_np[idx][:-1], out=pos[1:])
-            start[idx] = r * pad + pos
+    start = gather_start_rows(parts, costs_np, pad)
     if world_size == 1 and np.array_equal(start, offsets[:-1]):
         return flat  # already in original order
     src = np.repeat(start - offsets[:-1], costs_np) + np.arange(total, dtype=np.int64)

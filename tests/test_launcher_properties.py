@@ -1,0 +1,71 @@
+"""CPU: property tests (hypothesis) of the data-parallel launcher's host logic: LPT partition, sub-batch
+budgeting, the token-count rule against the C library, and the row map that restores the original order after the gather."""
+import ctypes
+
+import numpy as np
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from qwen3_asr_mlx_b200 import _lib, launcher
+
+costs_st = st.lists(st.integers(min_value=1, max_value=400), min_size=0, max_size=60)
+
+
+@settings(max_examples=200, deadline=None)
+@given(costs=costs_st, world=st.integers(min_value=1, max_value=8))
+def test_lpt_partition_covers_everything_once_and_is_balanced(costs, world):
+    parts = launcher.lpt_partition(costs, world)
+    assert len(parts) == world
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(len(costs)))
+    assert all(p == sorted(p) for p in parts)
+    loads = [sum(costs[i] for i in p) for p in parts]
+    if costs:
+        # greedy LPT: no rank exceeds the lightest one by more than the heaviest single item
+        assert max(loads) - min(loads) <= max(costs)
+    assert parts == launcher.lpt_partition(costs, world)  # deterministic: every rank computes the same assignment
+
+
+@settings(max_examples=200, deadline=None)
+@given(costs=costs_st, budget=st.integers(min_value=1, max_value=1000))
+def test_split_by_budget_keeps_order_and_budget(costs, budget):
+    idx = list(range(len(costs)))
+    subs = launcher.split_by_budget(idx, costs, budget)
+    assert [i for s in subs for i in s] == idx
+    for s in subs:
+        assert s and (len(s) == 1 or sum(costs[i] for i in s) <= budget)
+
+
+@settings(max_examples=300, deadline=None)
+@given(n=st.integers(min_value=160, max_value=20_000_000))
+def test_token_rule_matches_the_library(n):
+    lib = _lib.load()
+    frames, tokens = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.qasr_count_frames(n, ctypes.byref(frames)) == 0 and frames.value == n // 160
+    assert lib.qasr_count_tokens(None, frames.value, ctypes.byref(tokens)) == 0
+    assert tokens.value == launcher.tokens_for_samples(n)
+    full, rem = divmod(n // 160, 100)
+    assert tokens.value == 13 * full + (launcher.conv_output_length(rem) if rem else 0)
+
+
+@settings(max_examples=200, deadline=None)
+@given(costs=st.lists(st.integers(min_value=1, max_value=50), min_size=1, max_size=40), world=st.integers(min_value=1, max_value=6))
+def test_gather_row_map_restores_original_order(costs, world):
+    """Simulate the all-gathered buffer (rank r's rows at r * pad, its utterances back to back) and check that the row map
+    puts every utterance's rows back at its original offset."""
+    parts = launcher.lpt_partition(costs, world)
+    c = np.asarray(costs, dtype=np.int64)
+    per_rank = [int(c[p].sum()) if p else 0 for p in parts]
+    pad = max(per_rank)
+    flat = np.full(world * pad, -1, dtype=np.int64)  # each row holds (utterance id * 1000 + row within the utterance)
+    for r, p in enumerate(parts):
+        pos = r * pad
+        for i in p:
+            flat[pos: pos + costs[i]] = i * 1000 + np.arange(costs[i])
+            pos += costs[i]
+    start = launcher.gather_start_rows(parts, c, pad)
+    offsets = np.concatenate([[0], np.cumsum(c)])
+    src = np.repeat(start - offsets[:-1], c) + np.arange(int(c.sum()))
+    restored = flat[src]
+    want = np.concatenate([i * 1000 + np.arange(costs[i]) for i in range(len(costs))])
+    assert np.array_equal(restored, want)
