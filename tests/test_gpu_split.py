@@ -108,3 +108,30 @@ def test_transcribe_long_audio_segments(enc):
     emb, toffs, spans = shell.encode_long(x, 30.0)
     alone = np.array(enc.encode_audio_batch([x[spans[2][0]: spans[2][1]]])[0])
     assert np.array_equal(np.array(emb)[int(toffs[2]): int(toffs[3])], alone)
+
+
+def test_random_inputs_equal_host_twin(enc):
+    """80 random (length, chunk, search, frame) combinations, with silent stretches and constant signals (exact ties), against
+    the numpy twin -- which tests/test_model_shell.py pins to the reference's own function on the same kind of inputs."""
+    import torch
+
+    from qwen3_asr_mlx_b200.model import _find_split_points
+
+    rng = np.random.default_rng(2027)
+    for case in range(80):
+        n = int(rng.integers(1, 300_000))
+        frame = int(rng.choice([480, 480, 480, 160, 1000, 37, 7, 129]))
+        chunk = int(rng.integers(max(1, n // 20), max(2, n)))
+        search = int(rng.integers(0, 3 * chunk))
+        x = (rng.standard_normal(n) * np.abs(np.sin(np.arange(n) / rng.uniform(500, 9000)))).astype(np.float32)
+        if case % 5 == 0:
+            a = int(rng.integers(0, n))
+            x[a: a + int(rng.integers(1, 5000))] = 0.0
+        if case % 7 == 0:
+            x[:] = np.float32(0.25)
+        pts, energy = enc.find_split_points(torch.from_numpy(x).cuda(), chunk, search, frame, return_energy=True)
+        nf = n // frame
+        if nf:
+            want_e = np.sqrt(np.mean(x[: nf * frame].reshape(nf, frame) ** 2, axis=1)).astype(np.float32)
+            assert np.array_equal(energy.cpu().numpy().view(np.uint32), want_e.view(np.uint32)), (case, n, frame)
+        assert pts == _find_split_points(x, chunk, search, frame), (case, n, chunk, search, frame)

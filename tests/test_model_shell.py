@@ -57,3 +57,35 @@ def test_result_and_language_helpers():
     assert shell._resolve_language("Klingon") == "Klingon"
     with pytest.raises(ValueError):
         Qwen3ASR._as_samples(np.zeros((2, 100), dtype=np.float32))
+
+
+def _reference_split_fn():
+    """The reference's own _find_split_points, extracted with ast (its module imports mlx); authoring container only."""
+    import ast
+
+    path = "/root/reference/src/qwen3_asr_mlx/model.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present (GPU box)")
+    node = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "_find_split_points")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "reference_model_py", "exec"), ns)
+    return ns["_find_split_points"]
+
+
+def test_split_points_equal_the_reference_function_on_random_inputs():
+    """Beyond the committed golden cases: 150 random (length, chunk, search, frame) combinations, including chunk < search,
+    frames that do not divide the length, silence and constant segments (ties -> first minimum)."""
+    ref = _reference_split_fn()
+    rng = np.random.default_rng(2026)
+    for case in range(150):
+        n = int(rng.integers(1, 200_000))
+        frame = int(rng.choice([480, 480, 480, 160, 1000, 37]))
+        chunk = int(rng.integers(max(1, n // 20), max(2, n)))
+        search = int(rng.integers(0, 3 * chunk))
+        x = (rng.standard_normal(n) * np.abs(np.sin(np.arange(n) / rng.uniform(500, 9000)))).astype(np.float32)
+        if case % 5 == 0:
+            a = int(rng.integers(0, n))
+            x[a: a + int(rng.integers(1, 5000))] = 0.0          # exact ties inside a silent stretch
+        if case % 7 == 0:
+            x[:] = np.float32(0.25)                             # constant signal: every frame ties
+        assert _find_split_points(x, chunk, search, frame) == ref(x, chunk, search, frame), (case, n, chunk, search, frame)
