@@ -84,3 +84,23 @@ def test_package_filterbank_helpers(golden_dir):
     assert fb1 is fb2 and len(audio._mel_filterbank_cache) == 1
     assert fb1.shape == (audio.N_MELS, audio.N_FFT // 2 + 1)
     assert np.array_equal(fb1, np.load(os.path.join(golden_dir, "mel_filterbank.npy")))
+
+
+def test_oracle_equals_the_reference_run_verbatim_on_random_inputs():
+    """Beyond the 13 committed golden vectors: 40 random lengths / amplitudes / offsets through the reference's own
+    log_mel_spectrogram (oracle/mel_ref.py runs audio.py verbatim; authoring container only) -- bit-identical."""
+    from oracle import mel_ref
+
+    if not mel_ref.available():
+        pytest.skip("reference tree not present (GPU box)")
+    rng = np.random.default_rng(77)
+    for case in range(40):
+        n = int(rng.integers(160, 60000))
+        x = (rng.uniform(1e-4, 1.0) * rng.standard_normal(n) + rng.uniform(-0.2, 0.2)).astype(np.float32)
+        if case % 6 == 0:
+            x[int(rng.integers(0, n)):] = 0.0
+        want = np.asarray(mel_ref.log_mel_spectrogram(x), dtype=np.float32)
+        got = mel_np.log_mel_spectrogram(x)
+        assert got.shape == want.shape == (128, n // 160)
+        assert np.array_equal(got, want), (case, n)
+        assert np.abs(mel_np.log_mel_spectrogram_fast(x) - want).max() <= 1e-6
