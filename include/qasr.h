@@ -145,6 +145,14 @@ int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_sam
                            int32_t frame_samples, int64_t* points_out, int32_t max_points, int32_t* n_points_out,
                            float* energy_out_dev, void* stream);
 
+/* Final gather over NVLink peer memory (the only communication of the data-parallel path; the reference is
+ * single-device and has no counterpart).  local_dev: this rank's packed rows [n_rows, row_bytes]; dst_rows_dev: DEVICE array,
+ * final row index of every local row in the gathered matrix; peer_ptrs: HOST array of n_peers DEVICE pointers to every
+ * rank's output buffer (P2P-mapped, e.g. torch symmetric memory), this rank's own included.  row_bytes % 16 == 0.
+ * The caller synchronises the ranks before (buffers free) and after (writes landed). */
+int qasr_scatter_rows_to_peers(const void* local_dev, int64_t n_rows, int32_t row_bytes, const int64_t* dst_rows_dev,
+                               void* const* peer_ptrs, int32_t n_peers, void* stream);
+
 /* ---- constant tables, as the library builds them (for parity tests) ---- */
 int qasr_mel_filterbank(float* out_128x201);
 int qasr_hann_window(float* out_400);

@@ -18,6 +18,7 @@
 #include "encoder_kernels.cuh"
 #include "gemm_host.cuh"
 #include "mel.cuh"
+#include "peer_gather.cuh"
 #include "split.cuh"
 
 using namespace qasr;
@@ -1365,6 +1366,24 @@ int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_sam
   h->stats.kernel_launches++;
   QCUDA(h, cudaMemcpyAsync(points_out, h->d_points.p, static_cast<size_t>(n_bound) * 8, cudaMemcpyDeviceToHost, st));
   QCUDA(h, cudaStreamSynchronize(st));
+  return QASR_OK;
+}
+
+int qasr_scatter_rows_to_peers(const void* local_dev, int64_t n_rows, int32_t row_bytes, const int64_t* dst_rows_dev,
+                               void* const* peer_ptrs, int32_t n_peers, void* stream) {
+  if (n_rows < 0 || row_bytes <= 0 || row_bytes % 16 != 0 || !peer_ptrs || n_peers <= 0 || n_peers > kMaxPeers || n_rows > 0x7FFFFFFF)
+    return fail(nullptr, QASR_ERR_INVALID, "qasr_scatter_rows_to_peers: bad argument");
+  if (n_rows == 0) return QASR_OK;
+  if (!local_dev || !dst_rows_dev) return fail(nullptr, QASR_ERR_INVALID, "qasr_scatter_rows_to_peers: null pointer");
+  PeerPtrs pp{};
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_ptrs[i]) return fail(nullptr, QASR_ERR_INVALID, "qasr_scatter_rows_to_peers: null peer pointer");
+    pp.p[i] = peer_ptrs[i];
+  }
+  qasr_handle* h = nullptr;
+  scatter_rows_to_peers_kernel<<<static_cast<unsigned>(n_rows), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(local_dev), reinterpret_cast<const long long*>(dst_rows_dev), row_bytes / 16, pp, n_peers);
+  QCUDA(h, cudaGetLastError());
   return QASR_OK;
 }
 

@@ -73,13 +73,14 @@ EncodeFn = Callable[[List[int]], Tuple[torch.Tensor, np.ndarray]]
 
 def encode_sharded(encode_fn: EncodeFn, n_samples: Sequence[int], output_dim: int, rank: int, world_size: int,
                    tokens_per_call: int = 32768, gather: bool = True, group=None,
-                   dtype: torch.dtype = torch.float32) -> Tuple[Optional[torch.Tensor], np.ndarray, List[int]]:
+                   dtype: torch.dtype = torch.float32, peer_gather: Optional["PeerGather"] = None) -> Tuple[Optional[torch.Tensor], np.ndarray, List[int]]:
     """Encode utterances ``0..len(n_samples)-1`` data-parallel.
 
     ``encode_fn(indices)`` must return ``(embeddings (sum tokens, output_dim), token_offsets)`` for
     the utterances ``indices`` (in that order) on this rank's device.  Returns
     ``(all_embeddings or None, token_offsets (B+1,), my_indices)``: with ``gather=True`` every rank
-    receives the embeddings of ALL utterances in original order.
+    receives the embeddings of ALL utterances in original order (NCCL all-gather-v + one row gather, or, with a
+    ``PeerGather``, one scatter kernel over NVLink peer memory).
     """
     costs = [tokens_for_samples(int(n)) for n in n_samples]
     parts = lpt_partition(costs, world_size)
@@ -96,6 +97,8 @@ def encode_sharded(encode_fn: EncodeFn, n_samples: Sequence[int], output_dim: in
         return local, global_offsets, mine
     device = pieces[0].device if pieces else torch.device("cpu")
     local = torch.cat(pieces) if pieces else torch.zeros((0, output_dim), dtype=dtype, device=device)
+    if peer_gather is not None:  # NVLink peer-memory scatter (transfer + order restore in one kernel) instead of NCCL
+        return peer_gather.gather(local, parts, costs), global_offsets, mine
     return gather_embeddings(local, parts, costs, output_dim, rank, world_size, group), global_offsets, mine
 
 
@@ -139,3 +142,69 @@ def gather_embeddings(local: torch.Tensor, parts: List[List[int]], costs: Sequen
         return flat  # already in original order
     src = np.repeat(start - offsets[:-1], costs_np) + np.arange(total, dtype=np.int64)
     return flat.index_select(0, torch.from_numpy(src).to(flat.device, non_blocking=True))
+
+
+def scatter_dst_rows(my_indices: Sequence[int], costs: Sequence[int]) -> np.ndarray:
+    """Final row (in the original-order gathered matrix) of every local row of a rank that holds the utterances
+    ``my_indices`` back to back."""
+    costs_np = np.asarray([int(c) for c in costs], dtype=np.int64)
+    offsets = np.zeros(len(costs_np) + 1, dtype=np.int64)
+    np.cumsum(costs_np, out=offsets[1:])
+    if len(my_indices) == 0:
+        return np.zeros(0, dtype=np.int64)
+    idx = np.asarray(list(my_indices), dtype=np.int64)
+    n = costs_np[idx]
+    local_start = np.zeros(len(idx), dtype=np.int64)
+    np.cumsum(n[:-1], out=local_start[1:])
+    return np.repeat(offsets[idx] - local_start, n) + np.arange(int(n.sum()), dtype=np.int64)
+
+
+class PeerGather:
+    """Final gather through NVLink peer memory: every rank writes its rows into every rank's output buffer at their final
+    positions with ONE kernel (``qasr_scatter_rows_to_peers``), so the transfer and the restore of the original utterance
+    order are fused; no padded staging buffer, no NCCL collective on the data path (the only collective calls are the two
+    device-side barriers of the symmetric-memory handle).  Buffers are torch symmetric memory (P2P-mapped by the rendezvous).
+
+    One instance per process; ``capacity_rows`` bounds the gathered matrix.  Needs NVLink/P2P between the ranks' GPUs."""
+
+    def __init__(self, capacity_rows: int, output_dim: int, dtype: torch.dtype = torch.bfloat16, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.dim, self.dtype = int(output_dim), dtype
+        self.buf = symm.empty((int(capacity_rows), self.dim), dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.row_bytes = self.dim * self.buf.element_size()
+        if self.row_bytes % 16:
+            raise ValueError("row size must be a multiple of 16 bytes")
+        import ctypes
+
+        self._ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+
+    def gather(self, local: torch.Tensor, parts: List[List[int]], costs: Sequence[int]) -> torch.Tensor:
+        """``local``: this rank's rows (its utterances ``parts[rank]`` back to back).  Returns the gathered matrix in original
+        utterance order (a view of this rank's symmetric buffer, valid until the next ``gather``)."""
+        import ctypes
+
+        from . import _lib
+
+        total = int(sum(int(c) for c in costs))
+        if total > self.buf.shape[0]:
+            raise ValueError(f"gathered matrix has {total} rows, capacity is {self.buf.shape[0]}")
+        if local.dtype != self.dtype or local.shape[1] != self.dim:
+            raise ValueError("local rows have the wrong dtype / width")
+        local = local.contiguous()
+        dst = torch.from_numpy(scatter_dst_rows(parts[self.rank], costs)).to(local.device, non_blocking=True)
+        assert dst.numel() == local.shape[0], "token count mismatch between host rule and local rows"
+        stream = torch.cuda.current_stream()
+        self.handle.barrier(channel=0)  # every rank has finished reading the previous gather's result
+        _lib.check(self.lib.qasr_scatter_rows_to_peers(ctypes.c_void_p(local.data_ptr()), local.shape[0], self.row_bytes,
+                                                       ctypes.c_void_p(dst.data_ptr()), self._ptrs, self.world,
+                                                       ctypes.c_void_p(stream.cuda_stream)))
+        self.handle.barrier(channel=1)  # every rank's writes have landed
+        return self.buf[:total]

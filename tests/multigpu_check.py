@@ -2,8 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multigpu_check.py
 
-Every rank encodes its LPT share of a ragged batch, the final all-gather-v restores the original order, and
-rank 0 checks the gathered embeddings bit-for-bit against a single-GPU encode of the whole batch.
+Every rank encodes its LPT share of a ragged batch, the final gather (NCCL all-gather-v + row gather, and the NVLink
+peer-memory scatter kernel) restores the original order, and the gathered embeddings are checked bit-for-bit against each
+other on every rank and against a single-GPU encode of the whole batch on rank 0.
 """
 import os
 import sys
@@ -36,12 +37,16 @@ def main():
         return emb.tensor, toffs
 
     emb, offs, mine = launcher.encode_sharded(encode_fn, lengths, cfg.output_dim, rank, world, tokens_per_call=2048)
-    ok = True
+    # the same gather through NVLink peer memory (one scatter kernel, no NCCL collective on the data path), twice (buffer reuse)
+    pg = launcher.PeerGather(int(offs[-1]) + 64, cfg.output_dim, dtype=torch.float32)
+    for _ in range(2):
+        emb_p2p, offs2, _ = launcher.encode_sharded(encode_fn, lengths, cfg.output_dim, rank, world, tokens_per_call=2048, peer_gather=pg)
+    ok = bool(torch.equal(emb_p2p, emb)) and list(offs2) == list(offs)
     if rank == 0:
         ref, ref_offs = enc.encode_audio_batch(audios)
-        ok = bool(torch.equal(emb, ref.tensor)) and list(offs) == list(ref_offs)
+        ok = ok and bool(torch.equal(emb, ref.tensor)) and list(offs) == list(ref_offs)
         print(f"world={world} shares={[len(p) for p in launcher.lpt_partition([launcher.tokens_for_samples(n) for n in lengths], world)]} "
-              f"tokens={int(offs[-1])} gathered==single-GPU: {ok}")
+              f"tokens={int(offs[-1])} gathered (NCCL and peer-memory scatter) == single-GPU: {ok}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -99,12 +99,25 @@ def main():
     run3(False)  # warm-up: workspaces, first-touch
     ms_fwd, _ = timed_max(lambda: run3(False), world)
     ms_all, (emb, offs, _) = timed_max(lambda: run3(True), world)
+    ms_p2p, same = None, None
+    if world > 1:  # the same gather as ONE scatter kernel over NVLink peer memory (launcher.PeerGather)
+        pg = launcher.PeerGather(int(offs[-1]), cfg.output_dim, dtype=torch.bfloat16)
+
+        def run3_p2p():
+            return launcher.encode_sharded(encode_fn, lengths, cfg.output_dim, rank, world, tokens_per_call=32768, gather=True,
+                                           dtype=torch.bfloat16, peer_gather=pg)
+
+        run3_p2p()
+        ms_p2p, (emb_p, _, _) = timed_max(run3_p2p, world)
+        same = bool(torch.equal(emb_p, emb))
     audio_s = sum(lengths) / SR
     per_rank_tokens = [sum(costs[i] for i in p) for p in parts]
     out["config3_mixed_length"] = {
         "utterances": len(lengths), "audio_seconds": audio_s, "tokens": int(offs[-1]), "tokens_per_rank_min_max": [min(per_rank_tokens), max(per_rank_tokens)],
         "ms_forward_only": ms_fwd, "audio_s_per_s_forward_only": audio_s / (ms_fwd / 1e3),
         "ms_with_final_gather": ms_all, "audio_s_per_s_with_final_gather": audio_s / (ms_all / 1e3),
+        "ms_with_peer_memory_gather": ms_p2p, "audio_s_per_s_with_peer_memory_gather": (audio_s / (ms_p2p / 1e3)) if ms_p2p else None,
+        "peer_memory_gather_equals_nccl_gather": same,
         "gathered_shape": list(emb.shape), "gathered_finite": bool(torch.isfinite(emb[::997].float()).all().item()),
         "gather_bytes_bf16": int(offs[-1]) * cfg.output_dim * 2,
         "note": "eager launches (every sub-batch has its own shape); host-side packing (torch.cat) inside the timed region",

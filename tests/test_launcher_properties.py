@@ -69,3 +69,21 @@ def test_gather_row_map_restores_original_order(costs, world):
     restored = flat[src]
     want = np.concatenate([i * 1000 + np.arange(costs[i]) for i in range(len(costs))])
     assert np.array_equal(restored, want)
+
+
+@settings(max_examples=200, deadline=None)
+@given(costs=st.lists(st.integers(min_value=1, max_value=50), min_size=1, max_size=40), world=st.integers(min_value=1, max_value=8))
+def test_peer_scatter_rows_tile_the_gathered_matrix(costs, world):
+    """The destination rows of all ranks' local rows (PeerGather) are a permutation of 0..total-1, and every utterance lands
+    at its original offset in order."""
+    parts = launcher.lpt_partition(costs, world)
+    offsets = np.concatenate([[0], np.cumsum(costs)])
+    seen = np.full(int(offsets[-1]), -1, dtype=np.int64)
+    for r, p in enumerate(parts):
+        dst = launcher.scatter_dst_rows(p, costs)
+        assert len(dst) == sum(costs[i] for i in p)
+        payload = np.concatenate([i * 1000 + np.arange(costs[i]) for i in p]) if p else np.zeros(0, dtype=np.int64)
+        assert (seen[dst] == -1).all()
+        seen[dst] = payload
+    want = np.concatenate([i * 1000 + np.arange(costs[i]) for i in range(len(costs))])
+    assert np.array_equal(seen, want)
