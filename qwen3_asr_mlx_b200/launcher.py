@@ -208,3 +208,42 @@ class PeerGather:
                                                        ctypes.c_void_p(stream.cuda_stream)))
         self.handle.barrier(channel=1)  # every rank's writes have landed
         return self.buf[:total]
+
+
+def window_shares(n_frames: int, world_size: int, window_frames: int = 800) -> List[Tuple[int, int]]:
+    """Frame ranges [a, b) of ONE utterance for every rank, cut on the attention-window grid (n_window_infer = 800 frames =
+    104 tokens, encoder.py:297-311) so that no window straddles two ranks; contiguous, as even as possible."""
+    n_win = (n_frames + window_frames - 1) // window_frames
+    base, extra = divmod(n_win, world_size)
+    out, w = [], 0
+    for r in range(world_size):
+        k = base + (1 if r < extra else 0)
+        out.append((min(w * window_frames, n_frames), min((w + k) * window_frames, n_frames)))
+        w += k
+    return out
+
+
+def encode_long_sharded(encoder, mel: torch.Tensor, rank: int, world_size: int, group=None,
+                        peer_gather: Optional["PeerGather"] = None, out_dtype: str = "float32") -> torch.Tensor:
+    """One long utterance (BASELINE config 4, single pass: the reference's default ``chunk_duration`` does not split a
+    20-minute file) on ``world_size`` GPUs.  ``mel`` is the utterance's full ``(128, T)`` log-mel -- every rank computes it
+    from the waveform (it carries the utterance-wide max of audio.py:275; 0.4 ms for 20 minutes) -- and each rank encodes
+    a contiguous share of whole attention windows: windows are independent given the mel, so the gathered result is
+    bit-identical to a single-GPU pass.  Returns the ``(n_tokens, output_dim)`` embeddings on every rank."""
+    T = int(mel.shape[1])
+    shares = window_shares(T, world_size)
+    a, b = shares[rank]
+    cfg = encoder.config
+    tdt = torch.bfloat16 if out_dtype in ("bfloat16", "bf16") else torch.float32
+    if b > a:
+        emb, _ = encoder.encode_batch([mel[:, a:b].contiguous()], out_dtype=out_dtype)
+        local = emb.tensor
+    else:
+        local = torch.zeros((0, cfg.output_dim), dtype=tdt, device=mel.device)
+    costs = [tokens_for_samples((hi - lo) * HOP) for lo, hi in shares]  # a share is a run of full windows (+ the tail)
+    parts = [[r] for r in range(world_size)]
+    if world_size == 1:
+        return local
+    if peer_gather is not None:
+        return peer_gather.gather(local, parts, costs)
+    return gather_embeddings(local, parts, costs, cfg.output_dim, rank, world_size, group)

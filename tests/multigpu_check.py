@@ -47,6 +47,20 @@ def main():
         ok = ok and bool(torch.equal(emb, ref.tensor)) and list(offs) == list(ref_offs)
         print(f"world={world} shares={[len(p) for p in launcher.lpt_partition([launcher.tokens_for_samples(n) for n in lengths], world)]} "
               f"tokens={int(offs[-1])} gathered (NCCL and peer-memory scatter) == single-GPU: {ok}")
+    # config 4, single pass: ONE long utterance, its attention windows sharded over the ranks (launcher.encode_long_sharded)
+    from qwen3_asr_mlx_b200 import log_mel_spectrogram
+
+    long_audio = synth(np.random.default_rng(4), 16000 * 95 + 777)
+    mel = log_mel_spectrogram(long_audio).tensor          # every rank computes the full mel (utterance-wide max)
+    whole = enc(mel).tensor[0]
+    pg2 = launcher.PeerGather(int(whole.shape[0]) + 8, cfg.output_dim, dtype=torch.float32)
+    sharded_nccl = launcher.encode_long_sharded(enc, mel, rank, world)
+    sharded_p2p = launcher.encode_long_sharded(enc, mel, rank, world, peer_gather=pg2)
+    ok_long = bool(torch.equal(sharded_nccl, whole)) and bool(torch.equal(sharded_p2p, whole))
+    if rank == 0:
+        print(f"config 4 single pass: {int(whole.shape[0])} tokens, window shares {launcher.window_shares(int(mel.shape[1]), world)}, "
+              f"sharded == single-GPU: {ok_long}")
+    ok = ok and ok_long
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -146,7 +146,23 @@ def main():
     ms4, (emb4, offs4, _) = timed_max(run4, world)
     out["config4_20min_chunked"] = {"segments": len(segs), "segment_seconds_min_max": [min(seg_len) / SR, max(seg_len) / SR], "tokens": int(offs4[-1]),
                                     "ms": ms4, "audio_s_per_s": 1200.0 / (ms4 / 1e3), "finite": bool(torch.isfinite(emb4.float()).all().item())}
-    if rank == 0:  # the default chunk_duration (1200 s) path: one utterance, 150 attention windows, one GPU
+    # the default chunk_duration (1200 s) path: ONE utterance, single pass, its 150 attention windows sharded over the ranks
+    if world > 1:
+        from qwen3_asr_mlx_b200 import log_mel_spectrogram
+
+        pg4 = launcher.PeerGather(15600, cfg.output_dim, dtype=torch.bfloat16)
+
+        def run4_single_pass():
+            mel = log_mel_spectrogram(xd).tensor  # every rank: full mel with the utterance-wide max (audio.py:275)
+            return launcher.encode_long_sharded(enc, mel, rank, world, peer_gather=pg4, out_dtype="bfloat16")
+
+        for _ in range(2):
+            run4_single_pass()
+        ms4s, emb4s = timed_max(run4_single_pass, world)
+        out["config4_20min_single_pass_sharded"] = {"ms": ms4s, "audio_s_per_s": 1200.0 / (ms4s / 1e3), "tokens": int(emb4s.shape[0]),
+                                                    "windows_per_rank": [-(-(b - a) // 800) for a, b in launcher.window_shares(120000, world)],
+                                                    "note": "mel on every rank + window share + peer-memory gather, eager launches"}
+    if rank == 0:  # the same on one GPU
         so = np.array([0, len(x)], dtype=np.int64)
         o = torch.empty((15600, cfg.output_dim), dtype=torch.bfloat16, device="cuda")
         for _ in range(3):

@@ -87,3 +87,17 @@ def test_peer_scatter_rows_tile_the_gathered_matrix(costs, world):
         seen[dst] = payload
     want = np.concatenate([i * 1000 + np.arange(costs[i]) for i in range(len(costs))])
     assert np.array_equal(seen, want)
+
+
+@settings(max_examples=200, deadline=None)
+@given(T=st.integers(min_value=1, max_value=200_000), world=st.integers(min_value=1, max_value=8))
+def test_window_shares_tile_the_utterance_on_the_window_grid(T, world):
+    shares = launcher.window_shares(T, world)
+    assert len(shares) == world and shares[0][0] == 0 and shares[-1][1] == T
+    for (a, b), (c, d) in zip(shares[:-1], shares[1:]):
+        assert b == c and a <= b
+    assert all(a % 800 == 0 for a, _ in shares if a < T)
+    # the token counts of the shares add up to the utterance's (no window is cut)
+    assert sum(launcher.tokens_for_samples((b - a) * 160) for a, b in shares if b > a) == launcher.tokens_for_samples(T * 160)
+    n_win = [-(-(b - a) // 800) for a, b in shares]
+    assert max(n_win) - min(n_win) <= 1
