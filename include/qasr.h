@@ -10,6 +10,10 @@
  *   qasr_set_weight      load_encoder_weights / model.load_weights  src/qwen3_asr_mlx/encoder.py:330-359
  *   qasr_count_tokens    AudioEncoder._conv_output_length + chunking src/qwen3_asr_mlx/encoder.py:197-207,258-268
  *   qasr_destroy         Qwen3ASR.close()                           src/qwen3_asr_mlx/model.py:261-269
+ *   qasr_find_split_points   _find_split_points (long-audio feeder) src/qwen3_asr_mlx/model.py:454-513
+ *   qasr_prepare_inputs  prepare_inputs (consumer of the output)    src/qwen3_asr_mlx/generate.py:20-81
+ *   qasr_scatter_rows_to_peers   final gather of the data-parallel launcher over NVLink peer memory (no reference counterpart)
+ *   (decoder prefill: include/qasr_decoder.h)
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * qasr_status; nothing throws or exits; qasr_last_error() gives the message for the last failure.
