@@ -23,6 +23,24 @@ def _expected():
     return torch.cat(rows)
 
 
+class _FakeEncoder:
+    """encode_batch([mel]) -> one row per token, holding the first frame value of the token's chunk and the token's index
+    within the chunk (tokens follow the reference's count rule)."""
+
+    class config:
+        output_dim = DIM
+
+    def encode_batch(self, mels, out_dtype="float32"):
+        from qwen3_asr_mlx_b200._array import DeviceArray
+
+        mel = mels[0]
+        rows = []
+        for f0 in range(0, mel.shape[1], 100):
+            n = launcher.conv_output_length(min(100, mel.shape[1] - f0))
+            rows.append(torch.stack([mel[0, f0] + torch.zeros(DIM) + 0.01 * t for t in range(n)]))
+        return DeviceArray(torch.cat(rows)), None
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -37,6 +55,12 @@ def _worker(rank, world, port, q):
 
         emb, offs, mine = launcher.encode_sharded(fake_encode, N_SAMPLES, DIM, rank, world, tokens_per_call=200)
         ok = bool(torch.equal(emb, _expected())) and int(offs[-1]) == emb.shape[0]
+        # one long utterance sharded by attention windows (config 4, single pass): a fake encoder whose token rows carry the
+        # absolute frame of their chunk, so any mis-cut or mis-ordered share shows
+        T = 800 * 5 + 333
+        mel = torch.arange(T, dtype=torch.float32)[None, :].repeat(4, 1)
+        long_emb = launcher.encode_long_sharded(_FakeEncoder(), mel, rank, world)
+        ok = ok and bool(torch.equal(long_emb, _FakeEncoder().encode_batch([mel])[0].tensor))
         q.put((rank, ok, mine))
     finally:
         dist.destroy_process_group()
