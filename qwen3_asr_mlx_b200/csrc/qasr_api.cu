@@ -33,6 +33,12 @@ constexpr int kStemC = 480;
 constexpr int kStemGroupDefault = 1024;
 constexpr int kGemmStages = 4;
 constexpr int kPairStages = 6;  // CTA-pair kernels stage half of B per CTA: 32 KB / stage
+// Small batches (a single utterance: BASELINE config 1) leave most SMs without a 256-wide tile; below kSmallMRows rows the
+// dense GEMMs run as 128 x 64 single-CTA tiles (4x the CTAs streaming weights).  Per-element arithmetic is unchanged (same
+// K order), so results stay bit-identical to the wide tiles (tests: batch == loop of singles).
+constexpr int kSmallN = 64;
+constexpr int kSmallStages = 6;  // 24 KB / stage
+constexpr int kSmallMRows = 1024;
 
 inline uint16_t f32_to_bf16(float f) {
   uint32_t u;
@@ -61,6 +67,7 @@ struct DevBuf {
 // (each CTA loads half of the B rows: box = BLOCK_N / 2 rows).
 struct WeightMaps {
   CUtensorMap m1, m2;
+  CUtensorMap ms;  // small-M kernel: 64-row B boxes (dense weights only)
 };
 
 struct LayerWeights {
@@ -91,6 +98,7 @@ struct qasr_handle {
   bool conv1_fp32 = false;  // QASR_CONV1_FP32=1 selects the CUDA-core fp32-weight conv1 (A/B testing)
   bool attn_tc = true;      // QASR_ATTN_TC=0 selects the mma.sync attention kernel instead of the tcgen05 one
   bool cta_pair = true;     // QASR_CTA_PAIR=0 selects the single-CTA (cta_group::1) GEMM kernels
+  bool small_tiles = true;     // QASR_SMALL_TILES=0 keeps the 256-wide tiles for small batches too
   bool conv_tail_skip = true;  // QASR_CONV_TAIL_SKIP=0 issues the MMAs over the zero-filled half of a tap's last K block too
   qasr_stats stats{};
 
@@ -329,7 +337,8 @@ int build_weight_maps(qasr_handle* h) {
   std::string e;
   const int D = c.d_model, F = c.encoder_ffn_dim;
   auto rows = [&](WeightMaps& m, const void* w, uint64_t n, uint64_t k) {
-    return make_tmap_rows(&m.m1, w, n, k, k, 256, &e) && make_tmap_rows(&m.m2, w, n, k, k, 128, &e);
+    return make_tmap_rows(&m.m1, w, n, k, k, 256, &e) && make_tmap_rows(&m.m2, w, n, k, k, 128, &e) &&
+           make_tmap_rows(&m.ms, w, n, k, k, kSmallN, &e);
   };
   auto conv = [&](WeightMaps& m, const void* w) {
     return make_tmap_conv_w(&m.m1, w, kStemC, kStemC, 240, &e) && make_tmap_conv_w(&m.m2, w, kStemC, kStemC, 120, &e);
@@ -486,7 +495,8 @@ int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, 
     toutp = &tout;
   }
   ProfScope ps(h, cat, st, 2.0 * M * N * K, 0.0);
-  if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI, 2>(ta, tw.m2, p, st, toutp)));
+  if (h->small_tiles && M <= kSmallMRows) QCUDA(h, (launch_gemm<kSmallN, kSmallStages, A_ROWS, EPI, 1>(ta, tw.ms, p, st, toutp)));
+  else if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI, 2>(ta, tw.m2, p, st, toutp)));
   else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI, 1>(ta, tw.m1, p, st, toutp)));
   return QASR_OK;
 }
@@ -646,7 +656,8 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
       p.row_map = static_cast<const int*>(ln.d_rowmap.p) + c0 * kTokensPerChunk;
       p.pe = h->pe; p.pe_period = kTokensPerChunk;
       ProfScope ps(h, QASR_PROF_CONV_OUT, st, 2.0 * g * kTokensPerChunk * D * 16 * kStemC, 0.0);
-      if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_CONVOUT_PACK, 2>(ln.tm_flat3, h->tm_convout_w.m2, p, st)));
+      if (h->small_tiles && g * kTokensPerChunk <= kSmallMRows) QCUDA(h, (launch_gemm<kSmallN, kSmallStages, A_ROWS, EPI_CONVOUT_PACK, 1>(ln.tm_flat3, h->tm_convout_w.ms, p, st)));
+      else if (h->cta_pair) QCUDA(h, (launch_gemm<256, kPairStages, A_ROWS, EPI_CONVOUT_PACK, 2>(ln.tm_flat3, h->tm_convout_w.m2, p, st)));
       else QCUDA(h, (launch_gemm<256, kGemmStages, A_ROWS, EPI_CONVOUT_PACK, 1>(ln.tm_flat3, h->tm_convout_w.m1, p, st)));
     }
   }
@@ -793,6 +804,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   if (const char* c1 = getenv("QASR_CONV1_FP32")) h->conv1_fp32 = atoi(c1) != 0;
   if (const char* cp = getenv("QASR_CTA_PAIR")) h->cta_pair = atoi(cp) != 0;
   if (const char* ts = getenv("QASR_CONV_TAIL_SKIP")) h->conv_tail_skip = atoi(ts) != 0;
+  if (const char* sm = getenv("QASR_SMALL_TILES")) h->small_tiles = atoi(sm) != 0;
   if (const char* at = getenv("QASR_ATTN_TC")) h->attn_tc = atoi(at) != 0;
   if (const char* sg = getenv("QASR_STEM_GROUP")) {
     const int v = atoi(sg);
