@@ -1,2 +1,3 @@
-"""Two-line stand-in for the `mlx` package so that the reference's numpy-only audio.py imports.
-TEST INFRASTRUCTURE ONLY (used by oracle/mel_ref.py inside the authoring container)."""
+"""Stand-in for the `mlx` package (TEST INFRASTRUCTURE ONLY, authoring container): torch-CPU fp32 implementations of
+the `mlx.core` / `mlx.nn` calls the reference makes, so that /root/reference/src/qwen3_asr_mlx imports and runs
+unmodified (oracle/mel_ref.py, oracle/reference_ref.py)."""

@@ -8,7 +8,9 @@ MLX semantics encoded here: Linear y = x W^T (no biases in this module); nn.RMSN
 nn.RoPE(dims, traditional=False, base): frequencies base^(-2i/dims), pairs (i, i + dims/2) ("rotate half"), position = offset + t;
 mx.fast.scaled_dot_product_attention broadcasts each KV head over n_heads / n_kv_heads query heads (GQA) and applies
 softmax(scale q k^T + mask) v with an fp32 softmax; the additive -1e9 causal mask equals masking in fp32.
-tests/test_oracle_upstream.py pins this restatement against transformers' Qwen3 implementation (the model authors' code).
+PINNED: tests/test_reference_pin.py compares logits / cached keys / values with tests/golden/decoder_reference.npz, the
+outputs of the reference's own decoder.py executed unmodified (oracle/reference_ref.py), <= 1e-5; tests/test_oracle_decoder.py
+additionally pins it against transformers' Qwen3 implementation (the model authors' code).
 """
 from __future__ import annotations
 

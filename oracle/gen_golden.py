@@ -3,10 +3,17 @@
 mel_*.npz     : inputs and outputs of the REFERENCE's own log_mel_spectrogram executed verbatim
                 (oracle/mel_ref.py) -> these pin oracle/mel_np.py and the CUDA mel kernels.
 mel_filterbank.npy : the reference's _get_mel_filterbank().
-encoder_small.npz  : oracle/encoder_np.py (fp64) output for a small seeded configuration.  NOT
-                reference-pinned (MLX cannot run here); a drift anchor for the two restatements.
+encoder_small.npz  : oracle/encoder_np.py (fp64) output for a small seeded configuration; a drift anchor for
+                the two restatements.
+encoder_reference.npz, decoder_reference.npz, prompt_reference.npz, language_map_reference.json :
+                outputs of the REFERENCE's own encoder.py / decoder.py / generate.prepare_inputs /
+                tokenizer.build_prompt / model.LANGUAGE_MAP executed unmodified behind the torch-backed MLX stand-in
+                (oracle/reference_ref.py) -> these pin oracle/encoder_{torch,np}.py, decoder_torch.py, prompt_np.py
+                and the CUDA path.  Inputs are regenerated from seeds by tests/reference_cases.py (shared with the
+                tests); a float64 checksum of every input is stored beside the output.
 
-    python oracle/gen_golden.py
+    python oracle/gen_golden.py               # everything
+    python oracle/gen_golden.py reference     # only the *_reference fixtures of encoder / decoder / prompt
 """
 from __future__ import annotations
 
@@ -34,9 +41,54 @@ def synth(rng, n):
     return np.clip(x, -1, 1).astype(np.float32)
 
 
+def gen_reference_fixtures():
+    """Run the reference's encoder / decoder / prepare_inputs verbatim on the seeded cases of tests/reference_cases.py."""
+    import json
+
+    from oracle import reference_ref
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reference_cases as rc
+
+    assert reference_ref.available(), "needs /root/reference"
+    out = {}
+    for group, (cfg, params) in rc.encoder_groups().items():
+        enc = reference_ref.build_encoder(params, cfg)
+        for name, mel in rc.encoder_inputs(group).items():
+            out[f"{group}/{name}/emb"] = reference_ref.encoder_forward(params, cfg, mel, enc)
+            out[f"{group}/{name}/checksum"] = np.array(rc.checksum(mel))
+            print("encoder", group, name, mel.shape, out[f"{group}/{name}/emb"].shape, flush=True)
+        del enc, params
+    np.savez_compressed(os.path.join(GOLDEN, "encoder_reference.npz"), **out)
+
+    out = {}
+    for group, (cfg, params) in rc.decoder_groups().items():
+        dec = reference_ref.build_decoder(params, cfg)
+        for name, emb in rc.decoder_inputs(group).items():
+            r = reference_ref.decoder_prefill(params, cfg, emb, dec)
+            for k in ("logits", "keys", "values"):
+                out[f"{group}/{name}/{k}"] = r[k]
+            out[f"{group}/{name}/checksum"] = np.array(rc.checksum(emb))
+            print("decoder", group, name, emb.shape, r["logits"].shape, r["keys"].shape, flush=True)
+    np.savez_compressed(os.path.join(GOLDEN, "decoder_reference.npz"), **out)
+
+    out = {}
+    pkg = reference_ref.package()
+    for name, (audio, lang_tokens, table) in rc.prompt_cases().items():
+        ids = pkg.build_prompt(audio.shape[1], lang_tokens)  # the reference's own tokenizer.build_prompt (tokenizer.py:56-86)
+        out[f"{name}/ids"] = np.array(ids, dtype=np.int64)
+        out[f"{name}/embeds"] = reference_ref.prepare_inputs(audio, ids, table)
+        out[f"{name}/checksum"] = np.array(rc.checksum(audio) + rc.checksum(table))
+    np.savez_compressed(os.path.join(GOLDEN, "prompt_reference.npz"), **out)
+    with open(os.path.join(GOLDEN, "language_map_reference.json"), "w") as f:
+        json.dump(dict(pkg.LANGUAGE_MAP), f, indent=0, sort_keys=True, ensure_ascii=False)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     assert mel_ref.available(), "needs /root/reference"
+    if len(sys.argv) > 1 and sys.argv[1] == "reference":
+        gen_reference_fixtures()
+        return
     rng = np.random.default_rng(20261018)
     cases = {}
     for n in (160, 161, 199, 200, 201, 319, 400, 2417, 16000):
@@ -108,6 +160,7 @@ def main():
             open(path, "wb").write(make_wav(**kw))
             la[name] = np.asarray(mel_ref.module().load_audio(path), dtype=np.float32)
     np.savez_compressed(os.path.join(GOLDEN, "load_audio_reference.npz"), **la)
+    gen_reference_fixtures()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

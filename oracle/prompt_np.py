@@ -3,8 +3,8 @@
 prepare_inputs: /root/reference/src/qwen3_asr_mlx/generate.py:20-81 — embed every id, then overwrite the
 audio-pad positions, in order, with the encoder rows cast to the embedding dtype; ValueError when the counts differ;
 plain embeddings when there is no pad.  build_prompt: tokenizer.py:16-86 (ids restated from the reference).
-UNPINNED by reference vectors (the reference code needs mlx); its tests pin the prompt ids
-(tests/test_tokenizer.py:48-73), which tests/test_prompt.py checks.
+PINNED: tests/golden/prompt_reference.npz holds the reference's own build_prompt ids and prepare_inputs outputs
+(oracle/reference_ref.py); tests/test_reference_pin.py requires exact equality.
 """
 import numpy as np
 

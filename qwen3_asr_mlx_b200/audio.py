@@ -118,7 +118,7 @@ def load_audio(path, target_sr: int = SAMPLE_RATE) -> np.ndarray:
     if path.suffix.lower() == ".wav":
         try:
             samples, rate = _read_wav_pcm(path)
-        except ValueError:
+        except Exception:  # any failure of the fast path falls through to soundfile, as in the reference (audio.py:189-193)
             samples = None
     if samples is None:
         import soundfile as sf  # optional dependency, exactly like the reference

@@ -43,14 +43,11 @@ class AudioEncoderConfig:
 
     @classmethod
     def from_pretrained(cls, model_path: str | Path) -> "AudioEncoderConfig":
-        """Read ``config.json`` from a local model directory and apply ``from_dict`` to it, as
-        ModelConfig.from_pretrained does in the reference (config.py:130-150).  Hub download is
-        out of scope here (no network); pass a local directory."""
-        path = Path(model_path)
-        if not path.is_dir():
-            raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
-        d = json.loads((path / "config.json").read_text(encoding="utf-8"))
-        return cls.from_dict(d)
+        """Read ``config.json`` from a local model directory, or from the hub when ``model_path`` is a repo id, and
+        apply ``from_dict`` to it, as ModelConfig.from_pretrained does in the reference (config.py:130-150)."""
+        from ._hub import config_dict
+
+        return cls.from_dict(config_dict(model_path))
 
 
 @dataclass
@@ -82,10 +79,9 @@ class TextDecoderConfig:
 
     @classmethod
     def from_pretrained(cls, model_path: str | Path) -> "TextDecoderConfig":
-        path = Path(model_path)
-        if not path.is_dir():
-            raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
-        return cls.from_dict(json.loads((path / "config.json").read_text(encoding="utf-8")))
+        from ._hub import config_dict
+
+        return cls.from_dict(config_dict(model_path))
 
 
 @dataclass
@@ -106,8 +102,7 @@ class ModelConfig:
 
     @classmethod
     def from_pretrained(cls, model_path: str | Path) -> "ModelConfig":
-        """``config.json`` of a local model directory (the reference also accepts a hub id; there is no network here)."""
-        path = Path(model_path)
-        if not path.is_dir():
-            raise FileNotFoundError(f"{model_path} is not a local model directory (hub download is not supported)")
-        return cls.from_dict(json.loads((path / "config.json").read_text(encoding="utf-8")))
+        """``config.json`` of a local model directory or of a hub repo id (reference config.py:130-150)."""
+        from ._hub import config_dict
+
+        return cls.from_dict(config_dict(model_path))

@@ -16,8 +16,11 @@
 // The MMA thread polls (test_wait: never suspends) its two kinds of pending work, S = QK^T of the next item and
 // O = PV of the oldest item, so neither can block the other.
 // The O(n^2) additive mask of the reference never exists: keys beyond the window length get
-// probability exactly 0.  Rows / keys of the 128-token tiles that lie beyond the window are
-// finite values of neighbouring tokens (or TMA zero fill) and never reach a stored output.
+// probability exactly 0.  Rows of the 128-token tiles that lie beyond the window belong to neighbouring windows /
+// utterances (or are stale workspace / TMA zero fill) and may hold ANYTHING, including the NaNs of a poisoned
+// utterance: masked score columns are overwritten with -inf before use, the V rows [len, 16*ceil(len/16)) that
+// the PV MMA multiplies by those exact zeros are zeroed in shared memory first (0 * NaN would be NaN), and query
+// rows beyond the window are never stored.  Utterances therefore stay isolated, like the reference's loop of singles.
 #pragma once
 #include "encoder_kernels.cuh"
 #include "ptx.cuh"
@@ -207,6 +210,14 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
         const float a0 = ex2(s3[2 * i]), a1 = ex2(s3[2 * i + 1]);
         sum += a0 + a1;
         p3[i] = ptx::pack_bf16x2(a0, a1);
+      }
+      if (len & 15) {
+        // zero the V rows the PV MMA reads beyond the window (row r of the 128B-swizzled tile is bytes [128 r, 128 r + 128))
+        uint8_t* vt = stage_base + (j % kAtStages) * kAtStageBytes + 2 * kAtTileBytes;
+        const int n16 = (16 - (len & 15)) * 8;  // 16-byte vectors, <= 120
+        const int t = quarter * 32 + lane;      // the 4 warps of a group cover all four quarters
+        if (t < n16) reinterpret_cast<uint4*>(vt + len * 128)[t] = make_uint4(0u, 0u, 0u, 0u);
+        ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA's async-proxy reads
       }
       const uint32_t tmem_p = tmem_base + lane_addr + st * kAtSlotCols + kAtPCol;
       ptx::tmem_st_32x16(tmem_p, p0);

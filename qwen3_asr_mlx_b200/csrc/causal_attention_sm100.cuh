@@ -15,8 +15,10 @@
 //               in TMEM; after the last step O / l -> bf16 -> global.  (One thread per row was latency-bound: 4.2 us
 //               per KV step.)
 // TMEM columns: S0 [0,128) | S1 [128,256) | P [256,320) (bf16 pairs) | O [320,448).
-// Keys beyond the prompt (rows of the next prompt, or TMA zero fill) and keys after the query get probability
-// exactly 0; query rows beyond the prompt are computed on finite garbage and never stored.
+// Keys beyond the prompt (rows of the next prompt, stale workspace or TMA zero fill -- possibly NaN) and keys after
+// the query get probability exactly 0: their score columns are overwritten with -inf, and on a prompt's last, partial
+// KV tile the V rows beyond the prompt are zeroed in shared memory before the PV MMA (0 * NaN would be NaN); query rows
+// beyond the prompt are never stored.  Prompts therefore stay isolated, like the reference's loop of singles.
 #pragma once
 #include "decoder_kernels.cuh"
 #include "ptx.cuh"
@@ -238,6 +240,17 @@ causal_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const AttnT
               ptx::tmem_st_32x32(tmem_o + 32 * c, o);
             }
           }
+        }
+        if (diag && tl.len < (kt + 1) * 128) {
+          // zero V rows [len - 128 kt, 128) of both 64-dim boxes (row r of a 128B-swizzled box is bytes [128 r, 128 r + 128))
+          uint8_t* vb = kv_base + static_cast<int>(step % kCtKvStages) * kCtKvStageBytes + 2 * kCtBoxBytes;
+          const int r0 = tl.len - kt * 128;                     // 1 .. 127
+          const int n16 = (128 - r0) * 8;                       // 16-byte vectors per box
+          for (int t = ch * 128 + r; t < 2 * n16; t += 256) {
+            const int box = t >= n16;
+            reinterpret_cast<uint4*>(vb + box * kCtBoxBytes + r0 * 128)[t - box * n16] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          ptx::fence_proxy_async_smem();
         }
         const uint32_t tmem_p = tmem_base + lane_addr + kCtPCol + ch * 32;  // 64 keys = 32 packed columns
         {

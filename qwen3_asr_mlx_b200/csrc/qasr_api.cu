@@ -872,9 +872,58 @@ void qasr_destroy(qasr_handle* h) {
   delete h;
 }
 
+// Shape every parameter must have (reference module construction, encoder.py:60-63,98-104,148-191; MLX layouts: Linear
+// (out, in), Conv2d (O, kH, kW, I)).  Returns the rank, 0 for a name the model does not have.
+static int expected_weight_shape(const qasr_config& c, const std::string& name, int64_t (&dims)[4]) {
+  const int64_t D = c.d_model, F = c.encoder_ffn_dim, C = kStemC, O = c.output_dim;
+  auto set = [&](std::initializer_list<int64_t> v) { int i = 0; for (int64_t d : v) dims[i++] = d; return static_cast<int>(v.size()); };
+  std::string leaf = name;
+  if (name.rfind("layers.", 0) == 0) {
+    const size_t dot = name.find('.', 7);
+    if (dot == std::string::npos || dot == 7) return 0;
+    for (size_t i = 7; i < dot; ++i) if (name[i] < '0' || name[i] > '9') return 0;
+    if (dot - 7 > 6 || std::stol(name.substr(7, dot - 7)) >= c.encoder_layers) return 0;
+    leaf = name.substr(dot + 1);
+    for (const char* proj : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+      if (leaf == std::string("self_attn.") + proj + ".weight") return set({D, D});
+      if (leaf == std::string("self_attn.") + proj + ".bias") return set({D});
+    }
+    for (const char* ln : {"self_attn_layer_norm", "final_layer_norm"})
+      if (leaf == std::string(ln) + ".weight" || leaf == std::string(ln) + ".bias") return set({D});
+    if (leaf == "fc1.weight") return set({F, D});
+    if (leaf == "fc1.bias") return set({F});
+    if (leaf == "fc2.weight") return set({D, F});
+    if (leaf == "fc2.bias") return set({D});
+    return 0;
+  }
+  if (leaf == "conv2d1.weight") return set({C, 3, 3, 1});
+  if (leaf == "conv2d2.weight" || leaf == "conv2d3.weight") return set({C, 3, 3, C});
+  if (leaf == "conv2d1.bias" || leaf == "conv2d2.bias" || leaf == "conv2d3.bias") return set({C});
+  if (leaf == "conv_out.weight") return set({D, 16 * C});
+  if (leaf == "ln_post.weight" || leaf == "ln_post.bias" || leaf == "proj1.bias") return set({D});
+  if (leaf == "proj1.weight") return set({D, D});
+  if (leaf == "proj2.weight") return set({O, D});
+  if (leaf == "proj2.bias") return set({O});
+  return 0;
+}
+
 int qasr_set_weight(qasr_handle* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
   if (!h || !name || !data || ndim < 1 || ndim > 4 || !shape) return fail(h, QASR_ERR_INVALID, "qasr_set_weight: bad argument");
   if (h->finalized) return fail(h, QASR_ERR_STATE, "weights already finalised");
+  {  // strict, like the reference's model.load_weights (encoder.py:358): unknown names and shape mismatches are errors
+    int64_t want[4];
+    const int rank = expected_weight_shape(h->cfg, name, want);
+    if (rank == 0) return fail(h, QASR_ERR_INVALID, std::string("received parameter not in model: ") + name);
+    bool same = rank == ndim;
+    for (int i = 0; same && i < rank; ++i) same = shape[i] == want[i];
+    if (!same) {
+      std::string msg = std::string("parameter ") + name + ": expected shape (";
+      for (int i = 0; i < rank; ++i) msg += (i ? ", " : "") + std::to_string(want[i]);
+      msg += ") but received (";
+      for (int i = 0; i < ndim; ++i) msg += (i ? ", " : "") + std::to_string(shape[i]);
+      return fail(h, QASR_ERR_INVALID, msg + ")");
+    }
+  }
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) {
     if (shape[i] <= 0) return fail(h, QASR_ERR_INVALID, "bad shape");

@@ -247,12 +247,12 @@ def _wrap_device_bf16(ptr: int, shape: Tuple[int, ...], device: torch.device, ow
 
 def load_decoder_weights(decoder: TextDecoder, model_path) -> None:
     """Load ``model.safetensors`` from a local directory: keys with the ``model.`` prefix, prefix stripped
-    (reference load_decoder_weights, decoder.py:257-291; hub download needs network and is not available)."""
+    (reference load_decoder_weights, decoder.py:257-291; a hub repo id is resolved with ``snapshot_download`` like there)."""
     from safetensors import safe_open
 
-    path = Path(model_path)
-    if not path.is_dir():
-        raise FileNotFoundError(f"{model_path}: pass a local model directory (hub download is not available offline)")
+    from ._hub import model_dir
+
+    path = model_dir(model_path)
 
     def items():
         with safe_open(str(path / "model.safetensors"), framework="pt") as f:

@@ -297,8 +297,9 @@ class AudioEncoder:
 def load_encoder_weights(model: AudioEncoder, model_path) -> None:
     """Populate ``model`` from ``<model_path>/model.safetensors`` (reference encoder.py:330-359):
     keys with prefix ``audio_tower.`` are kept and the prefix stripped; layouts are used as stored
-    (Conv2d weights (O, kH, kW, I)).  ``model_path`` must be a local directory (no network)."""
-    path = Path(model_path)
-    if not path.is_dir():
-        raise FileNotFoundError(f"{model_path}: hub download is not available; pass a local directory")
+    (Conv2d weights (O, kH, kW, I)).  ``model_path`` is a local directory or a hub repo id (``snapshot_download``,
+    encoder.py:342-344)."""
+    from ._hub import model_dir
+
+    path = model_dir(model_path)
     model.load_weights(_weights.load_safetensors(path / "model.safetensors"))

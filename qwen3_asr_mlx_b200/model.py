@@ -19,14 +19,17 @@ from .audio import SAMPLE_RATE, load_audio
 from .config import AudioEncoderConfig
 from .encoder import AudioEncoder, load_encoder_weights
 
-# ISO 639-1 hints -> the language names Qwen3-ASR prompts use.  Unknown hints pass through unchanged,
-# as in the reference's _resolve_language (model.py:359-366).
-LANGUAGE_MAP = {
-    "en": "English", "zh": "Chinese", "de": "German", "fr": "French", "es": "Spanish", "it": "Italian",
-    "pt": "Portuguese", "ru": "Russian", "ja": "Japanese", "ko": "Korean", "ar": "Arabic", "hi": "Hindi",
-    "nl": "Dutch", "tr": "Turkish", "pl": "Polish", "sv": "Swedish", "fa": "Persian", "id": "Indonesian",
-    "vi": "Vietnamese", "th": "Thai", "uk": "Ukrainian", "cs": "Czech", "el": "Greek", "he": "Hebrew",
-}
+# ISO 639-1 hints -> the language names Qwen3-ASR prompts use: the reference's table (model.py:28-96), entry for
+# entry (tests/test_reference_pin.py compares it with the reference's own dict).  Hints that are not in the table
+# pass through unchanged, as in the reference's _resolve_language (model.py:359-366).
+LANGUAGE_MAP = dict(pair.split(":") for pair in (
+    "af:Afrikaans ar:Arabic az:Azerbaijani be:Belarusian bg:Bulgarian bn:Bengali bs:Bosnian ca:Catalan cs:Czech cy:Welsh "
+    "da:Danish de:German el:Greek en:English es:Spanish et:Estonian fa:Persian fi:Finnish fr:French gl:Galician gu:Gujarati "
+    "he:Hebrew hi:Hindi hr:Croatian hu:Hungarian hy:Armenian id:Indonesian is:Icelandic it:Italian ja:Japanese ka:Georgian "
+    "kk:Kazakh kn:Kannada ko:Korean lt:Lithuanian lv:Latvian mk:Macedonian ml:Malayalam mn:Mongolian mr:Marathi ms:Malay "
+    "my:Burmese ne:Nepali nl:Dutch no:Norwegian pa:Punjabi pl:Polish pt:Portuguese ro:Romanian ru:Russian si:Sinhala "
+    "sk:Slovak sl:Slovenian sq:Albanian sr:Serbian sv:Swedish sw:Swahili ta:Tamil te:Telugu th:Thai tl:Filipino tr:Turkish "
+    "uk:Ukrainian ur:Urdu uz:Uzbek vi:Vietnamese zh:Chinese").split())
 
 
 @dataclass
@@ -83,11 +86,15 @@ class Qwen3ASR:
 
     @classmethod
     def from_pretrained(cls, model_id_or_path, decoder_backend: Optional[DecoderBackend] = None, **kwargs) -> "Qwen3ASR":
-        """Load ``config.json`` and the ``audio_tower.*`` weights of ``model.safetensors`` from a local
-        directory (reference model.py:151-188; hub download needs network and is not available)."""
-        path = Path(model_id_or_path)
-        if not path.is_dir():
-            raise FileNotFoundError(f"{model_id_or_path}: pass a local model directory (hub download is not available offline)")
+        """Load ``config.json`` and the ``audio_tower.*`` weights of ``model.safetensors`` from a local directory or,
+        when ``model_id_or_path`` is not one, from the HuggingFace Hub repo of that id (``snapshot_download``, imported
+        lazily; extra keyword arguments are forwarded to it) -- reference model.py:151-188.  ``device`` and
+        ``load_decoder`` are this implementation's own keywords."""
+        from ._hub import model_dir
+
+        device, load_decoder = kwargs.pop("device", None), kwargs.pop("load_decoder", False)
+        path = model_dir(model_id_or_path, **kwargs)
+        kwargs = {"device": device, "load_decoder": load_decoder}
         config = AudioEncoderConfig.from_pretrained(path)
         encoder = AudioEncoder(config, device=kwargs.get("device"))
         load_encoder_weights(encoder, path)
@@ -121,10 +128,14 @@ class Qwen3ASR:
         """mel + encoder for a batch -> (packed embeddings, token_offsets)."""
         return self._encoder.encode_audio_batch([self._as_samples(a) for a in audios])
 
-    def prefill_batch(self, audios: Sequence, language_tokens: Optional[Sequence[int]] = None):
+    def prefill_batch(self, audios: Sequence, language_tokens: Sequence[int]):
         """Waveforms -> first-token logits and KV cache for a whole batch, every stage on the device:
         mel + encoder (model.py:331-335), ``build_prompt`` (model.py:338-339), ONE ``prepare_inputs`` gather for all
         prompts (generate.py:266) and the decoder prefill (generate.py:269-275).  Needs a ``TextDecoder``.
+        ``language_tokens`` are the token ids of ``" " + language name`` (the reference always bakes one in:
+        ``Tokenizer.build_prompt(n, language=_resolve_language(...))``, default ``" English"``); the BPE tokenizer is outside
+        this path, so the caller encodes the name.  An empty list builds ``language<asr_text>`` with no name, which is NOT
+        a prompt the reference ever produces.
         Returns ``(last_logits (B, vocab), KVCache, prompt_offsets (B+1,), audio_token_offsets (B+1,))``."""
         from .generate import prepare_inputs
         from .tokenizer import build_prompt
@@ -175,6 +186,11 @@ class Qwen3ASR:
             samples = self._as_samples(audio)
             if len(samples) == 0:
                 return TranscriptionResult(text="", language="Unknown", duration=0.0)
+            if self._decoder_backend is None:  # checked before any GPU work is spent on the audio
+                raise NotImplementedError(
+                    "text generation is outside the B200 audio-encoding path: construct Qwen3ASR with a decoder_backend "
+                    "callable(audio_embeddings, n_audio_tokens, language, max_tokens, **sampling) -> str, or use encode()/encode_batch()"
+                )
             duration = len(samples) / SAMPLE_RATE
             lang = self._resolve_language(language)
             if duration > chunk_duration:  # strict '>', as in the reference (model.py:313)
@@ -184,11 +200,6 @@ class Qwen3ASR:
             else:
                 segments = [samples]
                 emb, toffs = self._encoder.encode_audio_batch(segments)
-            if self._decoder_backend is None:
-                raise NotImplementedError(
-                    "text generation is outside the B200 audio-encoding path: construct Qwen3ASR with a decoder_backend "
-                    "callable(audio_embeddings, n_audio_tokens, language, max_tokens, **sampling) -> str, or use encode()/encode_batch()"
-                )
             texts = []
             for i, seg in enumerate(segments):
                 seg_tokens = max(256, int(len(seg) / SAMPLE_RATE * 50)) if (max_tokens is None or len(segments) > 1) else max_tokens

@@ -262,7 +262,7 @@ def test_prefill_batch_shell_matches_manual_pipeline():
         single = d.prefill(x, return_cache=False)[0]
         assert np.array_equal(np.array(single)[0], np.array(last)[u])
     with pytest.raises(NotImplementedError):
-        Qwen3ASR(ecfg, enc).prefill_batch(xs)
+        Qwen3ASR(ecfg, enc).prefill_batch(xs, [22574])
     shell.close()
 
 
@@ -314,3 +314,30 @@ def test_prefix_consistency_like_cached_decode(small):
     for t in (0, 3, 63, 64, 127, 128, 200, 299):
         last = np.array(d.prefill(emb[: t + 1], return_cache=False)[0])[0]
         assert np.allclose(last, full[t], atol=1e-3), t
+
+
+def test_poisoned_prompt_stays_isolated(small):
+    """A NaN prompt between clean ones: the clean prompts' logits and KV rows are bit-identical to a clean batch (the last,
+    partial KV tile of a prompt over-reads the next prompt's rows; masked keys must contribute exactly 0)."""
+    cfg, params, d = small
+    lens = [37, 200, 65, 129, 1]
+    emb = _emb(123, sum(lens), cfg.hidden_size).cuda()
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    base, cache0 = d.prefill(emb, offs)
+    base = np.array(base)
+    k0, v0 = cache0.keys.float().cpu().numpy(), cache0.values.float().cpu().numpy()
+    for bad in range(len(lens)):
+        e2 = emb.clone()
+        e2[int(offs[bad]) + lens[bad] // 2] = float("nan")
+        got, cache = d.prefill(e2, offs)
+        got = np.array(got)
+        k1, v1 = cache.keys.float().cpu().numpy(), cache.values.float().cpu().numpy()
+        for u in range(len(lens)):
+            a, b = int(offs[u]), int(offs[u + 1])
+            if u == bad:
+                assert np.isnan(got[u]).all()
+            else:
+                assert np.array_equal(got[u], base[u]), (bad, u)
+                assert np.array_equal(k1[:, a:b], k0[:, a:b]) and np.array_equal(v1[:, a:b], v0[:, a:b])
+    # a clean call after the poisoned ones
+    assert np.array_equal(np.array(d.prefill(emb, offs)[0]), base)

@@ -402,3 +402,57 @@ def test_full_arch_config3_style_order_invariance(full):
     for pos, i in enumerate(perm):
         assert np.array_equal(e2[int(toffs2[pos]): int(toffs2[pos + 1])], e[int(toffs[i]): int(toffs[i + 1])]), i
     assert np.isfinite(e).all()
+
+
+def test_poisoned_utterance_stays_isolated(small):
+    """A NaN utterance poisons ITSELF only (the reference encodes utterances one at a time, model.py:239-250).  Attention tiles
+    over-read neighbouring rows of the packed batch by design; masked keys must contribute exactly 0 even when those rows are
+    NaN, and NaN rows left in the workspace by a poisoned call must not leak into a later, smaller call."""
+    cfg, params, enc = small
+    rng = np.random.default_rng(77)
+    # lengths chosen so that windows end at every residue mod 16 and the clean utterance's last window is short
+    lens = [16000 * 3 + 1234, 16000 * 9 + 4321, 160 * 57, 16000 * 11, 16000 * 2 + 99]
+    clean = [synth(rng, n) for n in lens]
+    solo = [np.array(enc.encode_audio_batch([x])[0]) for x in clean]
+    for bad_at in range(len(lens)):
+        xs = [x.copy() for x in clean]
+        xs[bad_at][len(xs[bad_at]) // 2] = np.nan
+        emb, toffs = enc.encode_audio_batch(xs)
+        e = np.array(emb)
+        for u in range(len(lens)):
+            got = e[int(toffs[u]): int(toffs[u + 1])]
+            if u == bad_at:
+                assert np.isnan(got).all()
+            else:
+                assert np.array_equal(got, solo[u]), (bad_at, u)
+        # a clean, smaller call right after the poisoned one (stale NaN rows beyond its last token)
+        for u in (2, 4):
+            assert np.array_equal(np.array(enc.encode_audio_batch([clean[u]])[0]), solo[u])
+    # +-inf samples behave the same way
+    xs = [x.copy() for x in clean]
+    xs[1][100] = np.inf
+    e = np.array(enc.encode_audio_batch(xs)[0])
+    toffs = enc.encode_audio_batch(xs)[1]
+    assert np.array_equal(e[: int(toffs[1])], solo[0]) and np.array_equal(e[int(toffs[2]): int(toffs[3])], solo[2])
+
+
+def test_weight_shapes_are_validated(small):
+    """qasr_set_weight is strict like the reference's model.load_weights (encoder.py:358): a PyTorch-layout conv weight
+    (O, I, kH, kW), a transposed Linear, a wrong rank or an unknown name is a ValueError, not silently wrong embeddings."""
+    from qwen3_asr_mlx_b200 import AudioEncoder
+
+    cfg, params, _ = small
+    for name, bad in [
+        ("conv2d2.weight", np.ascontiguousarray(params["conv2d2.weight"].transpose(0, 3, 1, 2))),  # (480,480,3,3)
+        ("conv2d1.weight", params["conv2d1.weight"].reshape(480, 1, 3, 3)),
+        ("layers.0.fc1.weight", np.ascontiguousarray(params["layers.0.fc1.weight"].T)),
+        ("proj2.bias", params["proj2.bias"][None]),
+        ("layers.2.fc1.bias", params["layers.0.fc1.bias"]),       # layer index beyond encoder_layers
+        ("conv_out.bias", np.zeros(cfg.d_model, np.float32)),      # conv_out has no bias (encoder.py:174-178)
+    ]:
+        enc = AudioEncoder(cfg)
+        p = dict(params)
+        p[name] = bad
+        with pytest.raises(ValueError):
+            enc.load_weights(p)
+        enc.close()

@@ -89,3 +89,54 @@ def test_split_points_equal_the_reference_function_on_random_inputs():
         if case % 7 == 0:
             x[:] = np.float32(0.25)                             # constant signal: every frame ties
         assert _find_split_points(x, chunk, search, frame) == ref(x, chunk, search, frame), (case, n, chunk, search, frame)
+
+
+def test_language_map_covers_reference_hints():
+    # hints the round-1 table lacked (ADVICE): they must resolve to the full names the reference prompts use
+    shell = object.__new__(Qwen3ASR)
+    for code, name in {"da": "Danish", "fi": "Finnish", "hu": "Hungarian", "bg": "Bulgarian", "ro": "Romanian", "ta": "Tamil",
+                       "ur": "Urdu", "af": "Afrikaans", "DA": "Danish"}.items():
+        assert shell._resolve_language(code) == name
+    assert len(LANGUAGE_MAP) == 67
+
+
+def test_hub_ids_resolve_through_huggingface_hub(tmp_path, monkeypatch):
+    """A non-directory argument is a hub repo id: snapshot_download / hf_hub_download are imported lazily and called like
+    the reference does (model.py:170-176, config.py:139-148, encoder.py:342-344)."""
+    import json
+
+    import huggingface_hub
+
+    from qwen3_asr_mlx_b200 import _hub
+    from qwen3_asr_mlx_b200.config import AudioEncoderConfig, ModelConfig, TextDecoderConfig
+
+    (tmp_path / "config.json").write_text(json.dumps({"audio_encoder_config": {"d_model": 256, "encoder_layers": 3}, "text_config": {}}))
+    calls = []
+    monkeypatch.setattr(huggingface_hub, "snapshot_download", lambda repo_id, **kw: calls.append(("snap", repo_id, kw)) or str(tmp_path))
+    monkeypatch.setattr(huggingface_hub, "hf_hub_download", lambda repo_id, filename, **kw: calls.append(("file", repo_id, filename)) or str(tmp_path / filename))
+    assert _hub.model_dir(tmp_path) == tmp_path and not calls
+    assert _hub.model_dir("org/some-model", revision="main") == tmp_path
+    assert calls == [("snap", "org/some-model", {"revision": "main"})]
+    cfg = AudioEncoderConfig.from_pretrained("org/some-model")
+    assert cfg.d_model == 256 and cfg.encoder_layers == 3 and calls[-1] == ("file", "org/some-model", "config.json")
+    assert ModelConfig.from_pretrained("org/some-model").audio_encoder.d_model == 256
+    assert TextDecoderConfig.from_pretrained(tmp_path).hidden_size == TextDecoderConfig().hidden_size
+
+
+def test_load_audio_falls_back_on_any_fast_path_failure(tmp_path, monkeypatch):
+    """A WAV whose fmt chunk is truncated makes the native reader fail with struct.error; like the reference
+    (audio.py:189-193: `except Exception`) the loader then tries soundfile instead of propagating."""
+    import struct
+    import sys
+    import types
+
+    from qwen3_asr_mlx_b200.audio import load_audio
+
+    body = b"fmt " + struct.pack("<I", 8) + b"\x01\x00\x01\x00\x80\x3e\x00\x00" + b"data" + struct.pack("<I", 4) + b"\0\0\0\0"
+    path = tmp_path / "bad.wav"
+    path.write_bytes(b"RIFF" + struct.pack("<I", 4 + len(body)) + b"WAVE" + body)
+    fake = types.ModuleType("soundfile")
+    fake.read = lambda p, dtype, always_2d: (np.full((10, 2), 0.5, dtype=np.float32), 16000)
+    monkeypatch.setitem(sys.modules, "soundfile", fake)
+    out = load_audio(path)
+    assert out.shape == (10,) and np.allclose(out, 0.5)

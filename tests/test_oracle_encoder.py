@@ -1,6 +1,7 @@
 """CPU: the two independent encoder restatements agree, and honour the reference's shape
 contract (reference tests/test_encoder.py:41-198).  The reference holds no numeric vectors for
-the encoder: numeric parity of the encoder is UNPINNED by the reference."""
+the encoder; numeric parity is pinned by tests/test_reference_pin.py, which compares these restatements with
+the reference's own encoder.py executed verbatim."""
 import os
 
 import numpy as np
