@@ -182,8 +182,9 @@ class array:
     def _bin(self, other, fn, reverse=False):
         o = _operand(other, self._t)
         a, b = (o, self._t) if reverse else (self._t, o)
-        if a.dtype == torch.bool and b.dtype == torch.bool and fn in (torch.mul, torch.add):
-            pass
+        if fn is torch.matmul and a.dtype != b.dtype:
+            dt = torch.promote_types(a.dtype, b.dtype)
+            a, b = a.to(dt), b.to(dt)
         return array(fn(a, b))
 
     def __add__(self, o): return self._bin(o, torch.add)

@@ -97,6 +97,17 @@ class Module:
         return self
 
 
+def _promote(x, *params):
+    """MLX type promotion: an fp32 activation meeting bf16 / fp16 parameters computes (and returns) fp32 -- this is why the
+    reference's activations are fp32 even with the bf16 checkpoint."""
+    t = mx._to_tensor(x)
+    dt = t.dtype
+    for p_ in params:
+        if p_ is not None:
+            dt = torch.promote_types(dt, p_.dtype)
+    return (t.to(dt),) + tuple(None if p_ is None else p_.to(dt) for p_ in params)
+
+
 def _uniform(shape, scale):
     return mx.array((torch.rand(shape) * 2.0 - 1.0) * scale)
 
@@ -110,7 +121,8 @@ class Linear(Module):
 
     def __call__(self, x):
         b = getattr(self, "bias", None)
-        return mx.array(F.linear(mx._to_tensor(x), self.weight._t, None if b is None else b._t))
+        t, w, bt = _promote(x, self.weight._t, None if b is None else b._t)
+        return mx.array(F.linear(t, w, bt))
 
 
 class Conv2d(Module):
@@ -123,10 +135,11 @@ class Conv2d(Module):
         self._stride, self._padding, self._dilation, self._groups = stride, padding, dilation, groups
 
     def __call__(self, x):
-        t = mx._to_tensor(x).permute(0, 3, 1, 2)                       # NHWC -> NCHW
-        w = self.weight._t.permute(0, 3, 1, 2)                          # (O,kH,kW,I) -> (O,I,kH,kW)
         b = getattr(self, "bias", None)
-        y = F.conv2d(t, w, None if b is None else b._t, stride=self._stride, padding=self._padding,
+        t, w, bt = _promote(x, self.weight._t, None if b is None else b._t)
+        t = t.permute(0, 3, 1, 2)                                       # NHWC -> NCHW
+        w = w.permute(0, 3, 1, 2)                                       # (O,kH,kW,I) -> (O,I,kH,kW)
+        y = F.conv2d(t, w, bt, stride=self._stride, padding=self._padding,
                      dilation=self._dilation, groups=self._groups)
         return mx.array(y.permute(0, 2, 3, 1))                           # back to NHWC
 
@@ -141,7 +154,8 @@ class LayerNorm(Module):
 
     def __call__(self, x):
         w, b = getattr(self, "weight", None), getattr(self, "bias", None)
-        return mx.array(F.layer_norm(mx._to_tensor(x), (self._dims,), None if w is None else w._t, None if b is None else b._t, self._eps))
+        t, wt, bt = _promote(x, None if w is None else w._t, None if b is None else b._t)
+        return mx.array(F.layer_norm(t, (self._dims,), wt, bt, self._eps))
 
 
 class RMSNorm(Module):
@@ -150,9 +164,9 @@ class RMSNorm(Module):
         self._eps = eps
 
     def __call__(self, x):
-        t = mx._to_tensor(x)
+        t, w = _promote(x, self.weight._t)
         tf = t.float()
-        return mx.array((tf * torch.rsqrt(tf.pow(2).mean(-1, keepdim=True) + self._eps)).to(t.dtype) * self.weight._t)
+        return mx.array((tf * torch.rsqrt(tf.pow(2).mean(-1, keepdim=True) + self._eps)).to(t.dtype) * w)
 
 
 class Embedding(Module):

@@ -347,6 +347,10 @@ def test_from_pretrained_local_checkpoint_and_shell(tmp_path, small):
         ref_enc.load_weights({k: bf16_round(v) for k, v in params.items()})
         assert np.array_equal(emb[0], np.array(ref_enc.encode_audio_batch([x])[0]))
         ref_enc.close()
+        # ... and against the ORACLE run on the checkpoint's own (bf16-rounded) tensors: what the reference computes after
+        # load_encoder_weights (encoder.py:330-359) on this file, fp32 activations
+        oracle = encoder_torch.encoder_forward({k: bf16_round(v) for k, v in params.items()}, cfg, mel_np.log_mel_spectrogram_fast(x))
+        assert rel_err(emb[0], oracle) <= EMB_TOL
         assert emb.shape == (1, enc.num_tokens(len(x) // 160), cfg.output_dim)
         r = model.transcribe(x, language="de")
         assert isinstance(r, TranscriptionResult) and r.text == "hello" and r.language == "German" and abs(r.duration - len(x) / 16000) < 1e-9
