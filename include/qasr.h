@@ -12,6 +12,7 @@
  *   qasr_destroy         Qwen3ASR.close()                           src/qwen3_asr_mlx/model.py:261-269
  *   qasr_find_split_points   _find_split_points (long-audio feeder) src/qwen3_asr_mlx/model.py:454-513
  *   qasr_prepare_inputs  prepare_inputs (consumer of the output)    src/qwen3_asr_mlx/generate.py:20-81
+ *   qasr_pack_audio      varlen packing of a batch of waveforms (no reference counterpart: it encodes one utterance per call)
  *   qasr_scatter_rows_to_peers   final gather of the data-parallel launcher over NVLink peer memory (no reference counterpart)
  *   (decoder prefill: include/qasr_decoder.h)
  *
@@ -148,6 +149,13 @@ int qasr_prepare_inputs(qasr_handle* h, const int32_t* input_ids, int64_t n_ids,
 int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_samples, int64_t chunk_samples, int64_t search_samples,
                            int32_t frame_samples, int64_t* points_out, int32_t max_points, int32_t* n_points_out,
                            float* energy_out_dev, void* stream);
+
+/* Varlen packing of device-resident waveforms (the batched layout above has no reference counterpart: the reference handles
+ * one utterance per call, model.py:239-250).  segments_dev: HOST array of `batch` DEVICE pointers, segment u holding
+ * sample_offsets[u+1] - sample_offsets[u] floats; packed_dev: device buffer of sample_offsets[batch] floats.  One table upload
+ * and one kernel, whatever the batch size. */
+int qasr_pack_audio(qasr_handle* h, const float* const* segments_dev, const int64_t* sample_offsets, int32_t batch,
+                    float* packed_dev, void* stream);
 
 /* Final gather over NVLink peer memory (the only communication of the data-parallel path; the reference is
  * single-device and has no counterpart).  local_dev: this rank's packed rows [n_rows, row_bytes]; dst_rows_dev: DEVICE array,

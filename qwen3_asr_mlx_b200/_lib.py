@@ -84,6 +84,7 @@ _SIGNATURES = {
     "qasr_host_wait": (c_int, [c_void_p, c_int32]),
     "qasr_prepare_inputs": (c_int, [c_void_p, POINTER(c_int32), c_int64, c_void_p, c_int, c_int64, c_int32, c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p]),
     "qasr_find_split_points": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, POINTER(c_int64), c_int32, POINTER(c_int32), c_void_p, c_void_p]),
+    "qasr_pack_audio": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), c_int32, c_void_p, c_void_p]),
     "qasr_scatter_rows_to_peers": (c_int, [c_void_p, c_int64, c_int32, c_void_p, POINTER(c_void_p), c_int32, c_void_p]),
     "qasr_mel_filterbank": (c_int, [POINTER(c_float)]),
     "qasr_hann_window": (c_int, [POINTER(c_float)]),

@@ -157,6 +157,34 @@ def _as_waveform(audio, sample_rate: int) -> np.ndarray | torch.Tensor:
     return a
 
 
+def pack_waveforms(h, waves: Sequence) -> Tuple[torch.Tensor, np.ndarray]:
+    """Varlen-pack a batch of 1-D waveforms into ONE contiguous float32 device buffer + sample offsets, without a per-utterance
+    host loop of device copies: host arrays are concatenated on the host and uploaded with one H2D copy; device tensors that
+    already lie back to back in one allocation are used in place (zero copy); any other set of device tensors goes through
+    ``qasr_pack_audio`` (one pointer-table upload + one kernel, whatever the batch size)."""
+    lengths = [int(w.shape[0]) for w in waves]
+    soffs = runtime.offsets_array(lengths)
+    dev = h.torch_device
+    if len(waves) == 1:
+        return as_device_f32(waves[0], dev), soffs
+    if all(isinstance(w, np.ndarray) for w in waves):
+        host = np.concatenate([np.asarray(w, dtype=np.float32) for w in waves])
+        return torch.from_numpy(host).to(dev, non_blocking=True), soffs
+    tens = [w if (isinstance(w, torch.Tensor) and w.device == dev and w.dtype == torch.float32 and w.is_contiguous())
+            else as_device_f32(w, dev) for w in waves]
+    base = tens[0]
+    adjacent = all(t.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() for t in tens) and all(
+        tens[i + 1].data_ptr() == tens[i].data_ptr() + 4 * lengths[i] for i in range(len(tens) - 1))
+    if adjacent:
+        return torch.as_strided(base, (int(soffs[-1]),), (1,)), soffs
+    packed = torch.empty(int(soffs[-1]), dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+    h.check(h.lib.qasr_pack_audio(h.ptr, ptrs, runtime.i64_ptr(soffs), len(tens), ctypes.c_void_p(packed.data_ptr()), h.stream_ptr()))
+    # the sources must stay alive until the kernel has read them: they are referenced by `tens` until this frame returns and the
+    # caching allocator only hands their memory to later work on the same stream
+    return packed, soffs
+
+
 def log_mel_spectrogram_batch(audios: Sequence, device: Optional[int] = None) -> Tuple[DeviceArray, np.ndarray]:
     """Log-mel features of a batch of utterances in one launch.
 
@@ -173,15 +201,9 @@ def log_mel_spectrogram_batch(audios: Sequence, device: Optional[int] = None) ->
         if n < HOP_LENGTH:
             # the reference fails here with numpy's "zero-size array to reduction operation maximum"
             raise ValueError(f"zero-size array to reduction operation maximum which has no identity (audio of {n} samples < {HOP_LENGTH})")
-    soffs = runtime.offsets_array(lengths)
     foffs = runtime.offsets_array([n // HOP_LENGTH for n in lengths])
     with torch.cuda.device(h.torch_device):
-        if len(waves) == 1:
-            packed = as_device_f32(waves[0], h.torch_device)
-        else:
-            packed = torch.empty(int(soffs[-1]), dtype=torch.float32, device=h.torch_device)
-            for w, s, e in zip(waves, soffs[:-1], soffs[1:]):
-                packed[int(s):int(e)].copy_(as_device_f32(w, h.torch_device))
+        packed, soffs = pack_waveforms(h, waves)
         mel = torch.empty(int(foffs[-1]) * N_MELS, dtype=torch.float32, device=h.torch_device)
         h.check(h.lib.qasr_mel(h.ptr, ctypes.c_void_p(packed.data_ptr()), runtime.i64_ptr(soffs), len(waves),
                                ctypes.c_void_p(mel.data_ptr()), h.stream_ptr()))

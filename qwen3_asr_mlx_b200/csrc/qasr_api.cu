@@ -18,6 +18,7 @@
 #include "encoder_kernels.cuh"
 #include "gemm_host.cuh"
 #include "mel.cuh"
+#include "pack.cuh"
 #include "peer_gather.cuh"
 #include "split.cuh"
 
@@ -131,7 +132,7 @@ struct qasr_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf mel_scratch, io_in, io_out;
   DevBuf d_soffs, d_foffs, d_boffs, d_uttmax;
-  DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src, d_energy, d_points;
+  DevBuf dbg_stem, dbg_layer0, dbg_hidden, d_prompt_src, d_energy, d_points, d_pack;
   long long dbg_tokens = 0;
   // per-category CUDA-event profiling (qasr_set_profile)
   bool profile = false;
@@ -1428,6 +1429,43 @@ int qasr_find_split_points(qasr_handle* h, const float* audio_dev, int64_t n_sam
   QCUDA(h, cudaMemcpyAsync(points_out, h->d_points.p, static_cast<size_t>(n_bound) * 8, cudaMemcpyDeviceToHost, st));
   QCUDA(h, cudaStreamSynchronize(st));
   return QASR_OK;
+}
+
+int qasr_pack_audio(qasr_handle* h, const float* const* segments_dev, const int64_t* sample_offsets, int32_t batch,
+                    float* packed_dev, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  if (!segments_dev || !sample_offsets || !packed_dev || batch <= 0 || sample_offsets[0] != 0)
+    return fail(h, QASR_ERR_INVALID, "qasr_pack_audio: bad argument");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  const int B = batch;
+  std::vector<int> boffs(B + 1, 0);
+  for (int u = 0; u < B; ++u) {
+    const long long len = sample_offsets[u + 1] - sample_offsets[u];
+    if (len < 0 || (len > 0 && !segments_dev[u])) return fail(h, QASR_ERR_INVALID, "qasr_pack_audio: bad segment");
+    const long long nb = boffs[u] + (len + kPackFloatsPerCta - 1) / kPackFloatsPerCta;
+    if (nb > 0x7FFFFFFF) return fail(h, QASR_ERR_INVALID, "batch too large for one pack launch");
+    boffs[u + 1] = static_cast<int>(nb);
+  }
+  if (boffs[B] == 0) return QASR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // one table upload: [B pointers | B + 1 sample offsets | B + 1 block offsets]
+  const size_t bp = static_cast<size_t>(B) * 8, bs = static_cast<size_t>(B + 1) * 8, bb = static_cast<size_t>(B + 1) * 4;
+  if ((rc = dev_alloc(h, h->d_pack, bp + bs + bb + 16, false))) return rc;
+  if ((rc = pin_begin(h, bp + bs + bb + 64))) return rc;
+  uint8_t* pin = pin_take(h, bp + bs + bb);
+  if (!pin) return fail(h, QASR_ERR_STATE, "pinned staging arena too small");
+  memcpy(pin, segments_dev, bp);
+  memcpy(pin + bp, sample_offsets, bs);
+  memcpy(pin + bp + bs, boffs.data(), bb);
+  QCUDA(h, cudaMemcpyAsync(h->d_pack.p, pin, bp + bs + bb, cudaMemcpyHostToDevice, st));
+  uint8_t* d = static_cast<uint8_t*>(h->d_pack.p);
+  pack_segments_kernel<<<boffs[B], kPackThreads, 0, st>>>(reinterpret_cast<const float* const*>(d),
+                                                         reinterpret_cast<const long long*>(d + bp),
+                                                         reinterpret_cast<const int*>(d + bp + bs), B, packed_dev);
+  QCUDA(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  return pin_end(h, st);
 }
 
 int qasr_scatter_rows_to_peers(const void* local_dev, int64_t n_rows, int32_t row_bytes, const int64_t* dst_rows_dev,

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, runtime, weights as _weights
 from ._array import DeviceArray, as_device_f32
-from .audio import HOP_LENGTH, N_MELS, _as_waveform, SAMPLE_RATE
+from .audio import HOP_LENGTH, N_MELS, _as_waveform, SAMPLE_RATE, pack_waveforms
 from .config import AudioEncoderConfig
 
 
@@ -175,14 +175,8 @@ class AudioEncoder:
             base = offsets[-1]
             offsets.extend(base + int(v) for v in toffs[1:])
             return DeviceArray(torch.cat(pieces)), np.asarray(offsets, dtype=np.int64)
-        soffs = runtime.offsets_array(lengths)
         with torch.cuda.device(h.torch_device):
-            if len(waves) == 1:
-                packed = as_device_f32(waves[0], h.torch_device)
-            else:
-                packed = torch.empty(int(soffs[-1]), dtype=torch.float32, device=h.torch_device)
-                for w, s, e in zip(waves, soffs[:-1], soffs[1:]):
-                    packed[int(s):int(e)].copy_(as_device_f32(w, h.torch_device))
+            packed, soffs = pack_waveforms(h, waves)
             return self.encode_packed_audio(packed, soffs, out_dtype)
 
     def encode_packed_audio(self, packed_audio: torch.Tensor, soffs: np.ndarray, out_dtype: str = "float32",

@@ -50,6 +50,25 @@ def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
     return parts
 
 
+def contiguous_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Token-balanced split of the utterance list into ``world_size`` CONTIGUOUS runs: rank r gets the utterances whose
+    token prefix sum (mid-point) falls into the r-th equal share.  Imbalance is below one utterance per rank, like LPT on
+    mixed-length data, but every rank's rows form ONE contiguous block of the gathered (original-order) matrix, so the final
+    gather is a handful of large NVLink DMA copies (copy engines, no SM time) that overlap the next sub-batch's kernels
+    instead of a row scatter.  Deterministic; every rank computes the same assignment locally."""
+    c = np.asarray([int(v) for v in costs], dtype=np.int64)
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    total = int(c.sum())
+    if total == 0:
+        return parts
+    mid = np.cumsum(c) - c / 2.0
+    owner = np.minimum((mid * world_size / total).astype(np.int64), world_size - 1)
+    owner = np.maximum.accumulate(owner)  # monotone even with zero-cost utterances
+    for i, r in enumerate(owner):
+        parts[int(r)].append(i)
+    return parts
+
+
 def split_by_budget(indices: Sequence[int], costs: Sequence[int], budget: int) -> List[List[int]]:
     """Split one rank's share into consecutive sub-batches of at most ``budget`` tokens each
     (bounds the activation workspace of one libqasr call)."""
@@ -210,6 +229,109 @@ class PeerGather:
         return self.buf[:total]
 
 
+class PeerBlockGather:
+    """Final gather for CONTIGUOUS shares (``contiguous_partition`` / ``window_shares``): the gathered matrix lives in torch
+    symmetric memory on every rank; a rank's kernels write its rows straight into its own copy at their final position
+    (``rows()`` is passed as the encoder's ``out=``), and ``push()`` then copies that block into every peer's buffer with
+    plain device-to-device copies over NVLink on side streams (copy engines: no SM is taken from the GEMMs), ordered after
+    the producing kernels by an event.  The pushes of sub-batch k overlap the kernels of sub-batch k + 1; only the last
+    block's transfer is exposed.  ``finish()`` joins the side streams and runs the symmetric-memory barrier, after which
+    every rank holds all rows in original order.  No NCCL collective and no staging buffer on the data path."""
+
+    def __init__(self, capacity_rows: int, output_dim: int, dtype: torch.dtype = torch.bfloat16, group=None, n_streams: int = 4):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.dim, self.dtype = int(output_dim), dtype
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty((int(capacity_rows), self.dim), dtype=dtype, device=dev)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        # peers in a rotated order so that at any moment the ranks target different destinations
+        self.peers = [(self.rank + k) % self.world for k in range(1, self.world)]
+        self.peer_bufs = {p: self.handle.get_buffer(p, tuple(self.buf.shape), dtype) for p in self.peers}
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(n_streams, len(self.peers))))]
+        self.bytes_pushed = 0
+        self._pending = False
+
+    def begin(self) -> None:
+        """Every rank has finished reading the previous result (its buffer may be overwritten)."""
+        self.handle.barrier(channel=0)
+
+    def rows(self, row0: int, n: int) -> torch.Tensor:
+        return self.buf[row0: row0 + n]
+
+    def push(self, row0: int, n: int) -> None:
+        """Copy rows [row0, row0 + n) of the local buffer (already queued on the current stream) to every peer."""
+        if n <= 0 or not self.peers:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        src = self.buf[row0: row0 + n]
+        for k, p in enumerate(self.peers):
+            st = self.streams[k % len(self.streams)]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                self.peer_bufs[p][row0: row0 + n].copy_(src, non_blocking=True)
+        self.bytes_pushed += n * self.dim * self.buf.element_size() * len(self.peers)
+        self._pending = True
+
+    def finish(self, total_rows: int) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        if self._pending:
+            for st in self.streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
+            self._pending = False
+        self.handle.barrier(channel=1)  # every rank's blocks have landed everywhere
+        return self.buf[:total_rows]
+
+
+def encode_contiguous_sharded(encoder, packed_audio: torch.Tensor, n_samples: Sequence[int], rank: int, world_size: int,
+                              gather: Optional[PeerBlockGather] = None, tokens_per_call: int = 32768,
+                              out_dtype: str = "bfloat16"):
+    """BASELINE config 3 on ``world_size`` GPUs with the gather hidden behind the compute.
+
+    ``n_samples``: lengths of ALL utterances (original order); ``packed_audio``: THIS rank's share (``contiguous_partition``
+    over token counts), packed back to back on the device.  The share is encoded in consecutive sub-batches of at most
+    ``tokens_per_call`` tokens -- slices of ``packed_audio``, no host-side packing -- each writing its embeddings at their
+    final rows of the symmetric buffer and pushed to the peers while the next sub-batch computes.
+    Returns ``(embeddings, token_offsets (B+1,), my_indices)``; with ``gather=None`` the embeddings are this rank's rows only."""
+    costs = [tokens_for_samples(int(n)) for n in n_samples]
+    parts = contiguous_partition(costs, world_size)
+    mine = parts[rank]
+    offsets = np.zeros(len(costs) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(costs, dtype=np.int64), out=offsets[1:])
+    total = int(offsets[-1])
+    row_base = int(offsets[mine[0]]) if mine else 0
+    my_rows = sum(costs[i] for i in mine)
+    tdt = torch.bfloat16 if out_dtype in ("bfloat16", "bf16") else torch.float32
+    if gather is not None:
+        if total > gather.buf.shape[0] or gather.dtype != tdt:
+            raise ValueError("gather buffer too small or of the wrong dtype")
+        gather.begin()
+        local = gather.rows(row_base, my_rows)
+    else:
+        local = torch.empty((my_rows, encoder.config.output_dim), dtype=tdt, device=packed_audio.device)
+    sample_pos, row_pos = 0, 0
+    for sub in split_by_budget(mine, costs, tokens_per_call):
+        so = np.zeros(len(sub) + 1, dtype=np.int64)
+        np.cumsum([int(n_samples[i]) for i in sub], out=so[1:])
+        rows = sum(costs[i] for i in sub)
+        _, toffs = encoder.encode_packed_audio(packed_audio[sample_pos: sample_pos + int(so[-1])], so, out_dtype=out_dtype,
+                                               out=local[row_pos: row_pos + rows])
+        assert int(toffs[-1]) == rows, "token count mismatch between host rule and library"
+        if gather is not None:
+            gather.push(row_base + row_pos, rows)
+        sample_pos += int(so[-1])
+        row_pos += rows
+    if gather is not None:
+        return gather.finish(total), offsets, mine
+    return local, offsets, mine
+
+
 def window_shares(n_frames: int, world_size: int, window_frames: int = 800) -> List[Tuple[int, int]]:
     """Frame ranges [a, b) of ONE utterance for every rank, cut on the attention-window grid (n_window_infer = 800 frames =
     104 tokens, encoder.py:297-311) so that no window straddles two ranks; contiguous, as even as possible."""
@@ -224,7 +346,7 @@ def window_shares(n_frames: int, world_size: int, window_frames: int = 800) -> L
 
 
 def encode_long_sharded(encoder, mel: torch.Tensor, rank: int, world_size: int, group=None,
-                        peer_gather: Optional["PeerGather"] = None, out_dtype: str = "float32") -> torch.Tensor:
+                        peer_gather=None, out_dtype: str = "float32") -> torch.Tensor:
     """One long utterance (BASELINE config 4, single pass: the reference's default ``chunk_duration`` does not split a
     20-minute file) on ``world_size`` GPUs.  ``mel`` is the utterance's full ``(128, T)`` log-mel -- every rank computes it
     from the waveform (it carries the utterance-wide max of audio.py:275; 0.4 ms for 20 minutes) -- and each rank encodes
@@ -235,12 +357,21 @@ def encode_long_sharded(encoder, mel: torch.Tensor, rank: int, world_size: int, 
     a, b = shares[rank]
     cfg = encoder.config
     tdt = torch.bfloat16 if out_dtype in ("bfloat16", "bf16") else torch.float32
+    costs = [tokens_for_samples((hi - lo) * HOP) for lo, hi in shares]  # a share is a run of full windows (+ the tail)
+    if isinstance(peer_gather, PeerBlockGather):
+        # shares are contiguous row blocks: encode, then DMA the block into every peer's buffer (copy engines over NVLink)
+        row0 = sum(costs[:rank])
+        peer_gather.begin()
+        if b > a:
+            emb, _ = encoder.encode_batch([mel[:, a:b].contiguous()], out_dtype=out_dtype)
+            peer_gather.rows(row0, costs[rank]).copy_(emb.tensor)
+            peer_gather.push(row0, costs[rank])
+        return peer_gather.finish(sum(costs))
     if b > a:
         emb, _ = encoder.encode_batch([mel[:, a:b].contiguous()], out_dtype=out_dtype)
         local = emb.tensor
     else:
         local = torch.zeros((0, cfg.output_dim), dtype=tdt, device=mel.device)
-    costs = [tokens_for_samples((hi - lo) * HOP) for lo, hi in shares]  # a share is a run of full windows (+ the tail)
     parts = [[r] for r in range(world_size)]
     if world_size == 1:
         return local

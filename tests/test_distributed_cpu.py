@@ -41,6 +41,50 @@ class _FakeEncoder:
         return DeviceArray(torch.cat(rows)), None
 
 
+class _FakePackedEncoder:
+    """encode_packed_audio(audio, sample_offsets, out=...) writing one row per token: 1000 * (utterance id stored in the
+    utterance's first sample) + token index, i.e. the rows of _expected()."""
+
+    class config:
+        output_dim = DIM
+
+    def encode_packed_audio(self, audio, soffs, out_dtype="float32", out=None):
+        row = 0
+        for a, b in zip(soffs[:-1], soffs[1:]):
+            t = launcher.tokens_for_samples(int(b - a))
+            out[row: row + t] = torch.arange(t, dtype=torch.float32)[:, None] + 1000.0 * float(audio[int(a)]) + torch.zeros(DIM)
+            row += t
+        return out, np.concatenate([[0], np.cumsum([launcher.tokens_for_samples(int(b - a)) for a, b in zip(soffs[:-1], soffs[1:])])])
+
+
+class _GlooBlockGather:
+    """Stand-in for launcher.PeerBlockGather on CPU: same begin / rows / push / finish protocol, the pushes are delivered
+    with an all_gather_object in finish()."""
+
+    def __init__(self, rows):
+        self.buf = torch.full((rows, DIM), -1.0)
+        self.dtype = torch.float32
+        self.blocks = []
+
+    def begin(self):
+        dist.barrier()
+
+    def rows(self, row0, n):
+        return self.buf[row0: row0 + n]
+
+    def push(self, row0, n):
+        self.blocks.append((row0, self.buf[row0: row0 + n].clone()))
+
+    def finish(self, total):
+        everyone = [None] * dist.get_world_size()
+        dist.all_gather_object(everyone, self.blocks)
+        for blocks in everyone:
+            for row0, t in blocks:
+                self.buf[row0: row0 + t.shape[0]] = t
+        self.blocks = []
+        return self.buf[:total]
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -61,6 +105,17 @@ def _worker(rank, world, port, q):
         mel = torch.arange(T, dtype=torch.float32)[None, :].repeat(4, 1)
         long_emb = launcher.encode_long_sharded(_FakeEncoder(), mel, rank, world)
         ok = ok and bool(torch.equal(long_emb, _FakeEncoder().encode_batch([mel])[0].tensor))
+        # contiguous token-balanced shares + block pushes (the NVLink DMA gather of config 3): every rank packs ITS share only
+        costs = [launcher.tokens_for_samples(n) for n in N_SAMPLES]
+        share = launcher.contiguous_partition(costs, world)[rank]
+        packed = torch.cat([torch.full((N_SAMPLES[i],), float(i)) for i in share])
+        g = _GlooBlockGather(sum(costs))
+        for _ in range(2):  # the buffer is reused by a second gather
+            emb2, offs2, mine2 = launcher.encode_contiguous_sharded(_FakePackedEncoder(), packed, N_SAMPLES, rank, world, gather=g,
+                                                                    tokens_per_call=150, out_dtype="float32")
+            ok = ok and mine2 == share and bool(torch.equal(emb2, _expected())) and int(offs2[-1]) == emb2.shape[0]
+        loc, _, _ = launcher.encode_contiguous_sharded(_FakePackedEncoder(), packed, N_SAMPLES, rank, world, gather=None, out_dtype="float32")
+        ok = ok and bool(torch.equal(loc, _expected()[int(offs2[share[0]]): int(offs2[share[-1] + 1])]))
         q.put((rank, ok, mine))
     finally:
         dist.destroy_process_group()

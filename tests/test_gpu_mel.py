@@ -130,3 +130,39 @@ def test_non_finite_samples_poison_the_utterance_like_the_reference(audio_mod):
         blocks = [m[128 * int(foffs[u]): 128 * int(foffs[u + 1])] for u in range(3)]
         assert np.isnan(blocks[1]).all()
         assert np.isfinite(blocks[0]).all() and np.array_equal(blocks[0], blocks[2])
+
+
+def test_batch_packing_paths_agree(audio_mod):
+    """Varlen packing without a per-utterance host loop: a list of host arrays (one H2D), device tensors lying back to back
+    in one allocation (zero copy), scattered / misaligned device tensors (qasr_pack_audio: one table upload + one kernel) and a
+    host/device mix all give the bit-identical packed log-mel, and a 1024-utterance batch is a single pack launch."""
+    import torch
+
+    from qwen3_asr_mlx_b200 import runtime
+
+    rng = np.random.default_rng(21)
+    lens = [160, 16001, 47999, 300003, 1234, 160 * 33 + 7, 99998, 16000]
+    xs = [synth(rng, n) for n in lens]
+    want, foffs = audio_mod.log_mel_spectrogram_batch(xs)                       # host arrays
+    want = np.array(want)
+    scattered = [torch.from_numpy(x).cuda() for x in xs]                         # separate allocations
+    flat = torch.from_numpy(np.concatenate(xs)).cuda()
+    adjacent = list(flat.split(lens))                                            # views lying back to back
+    odd = torch.zeros(sum(lens) + 3 * len(lens), device="cuda")
+    misaligned, pos = [], 0
+    for x in xs:                                                                 # every segment starts 4 bytes off a 16 B boundary
+        pos += (-pos) % 4 + 1
+        odd[pos: pos + len(x)] = torch.from_numpy(x).cuda()
+        misaligned.append(odd[pos: pos + len(x)])
+        pos += len(x)
+    mixed = [scattered[i] if i % 2 else xs[i] for i in range(len(xs))]
+    for name, batch in (("scattered", scattered), ("adjacent", adjacent), ("misaligned", misaligned), ("mixed", mixed)):
+        got, fo = audio_mod.log_mel_spectrogram_batch(batch)
+        assert np.array_equal(fo, foffs) and np.array_equal(np.array(got), want), name
+    h = runtime.frontend_handle()
+    many = [torch.from_numpy(synth(rng, 16000)).cuda() for _ in range(8)] * 128  # 1024 one-second utterances
+    l0 = h.stats()["kernel_launches"]
+    got, fo = audio_mod.log_mel_spectrogram_batch(many)
+    assert h.stats()["kernel_launches"] - l0 == 3                                # pack + log-mel + normalise
+    g = np.array(got).reshape(1024, 128, 100)
+    assert np.array_equal(g[:8], g[8:16]) and np.array_equal(g[3], np.array(audio_mod.log_mel_spectrogram(many[3])))

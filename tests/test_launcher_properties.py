@@ -26,6 +26,19 @@ def test_lpt_partition_covers_everything_once_and_is_balanced(costs, world):
     assert parts == launcher.lpt_partition(costs, world)  # deterministic: every rank computes the same assignment
 
 
+@settings(max_examples=300, deadline=None)
+@given(costs=costs_st, world=st.integers(min_value=1, max_value=8))
+def test_contiguous_partition_is_ordered_contiguous_and_balanced(costs, world):
+    parts = launcher.contiguous_partition(costs, world)
+    assert len(parts) == world
+    assert [i for p in parts for i in p] == list(range(len(costs)))  # original order, every utterance once, contiguous runs
+    if costs:
+        share = sum(costs) / world
+        for p in parts:  # a run's load differs from the ideal share by less than one (the heaviest) utterance
+            assert abs(sum(costs[i] for i in p) - share) <= max(costs)
+    assert parts == launcher.contiguous_partition(costs, world)
+
+
 @settings(max_examples=200, deadline=None)
 @given(costs=costs_st, budget=st.integers(min_value=1, max_value=1000))
 def test_split_by_budget_keeps_order_and_budget(costs, budget):
