@@ -47,6 +47,22 @@ def main():
         ok = ok and bool(torch.equal(emb, ref.tensor)) and list(offs) == list(ref_offs)
         print(f"world={world} shares={[len(p) for p in launcher.lpt_partition([launcher.tokens_for_samples(n) for n in lengths], world)]} "
               f"tokens={int(offs[-1])} gathered (NCCL and peer-memory scatter) == single-GPU: {ok}")
+    # contiguous token-balanced shares + overlapped NVLink DMA block gather (the path bench.py measures at N > 1), twice
+    costs = [launcher.tokens_for_samples(n) for n in lengths]
+    share = launcher.contiguous_partition(costs, world)[rank]
+    packed = torch.from_numpy(np.concatenate([audios[i] for i in share])).cuda()
+    for dt, name in ((torch.float32, "float32"), (torch.bfloat16, "bfloat16")):
+        bg = launcher.PeerBlockGather(int(offs[-1]) + 16, cfg.output_dim, dtype=dt)
+        for _ in range(2):
+            emb_c, offs3, mine3 = launcher.encode_contiguous_sharded(enc, packed, lengths, rank, world, gather=bg, tokens_per_call=2048, out_dtype=name)
+        want = emb if dt == torch.float32 else None
+        if want is None:  # bf16 output: compare with a bf16 single-GPU encode of the whole batch (every rank computes it)
+            want = enc.encode_audio_batch(audios, out_dtype="bfloat16")[0].tensor
+        ok_c = bool(torch.equal(emb_c, want)) and list(offs3) == list(offs) and mine3 == share
+        if rank == 0:
+            print(f"contiguous shares {[len(p) for p in launcher.contiguous_partition(costs, world)]} + DMA block gather ({name}) == single-GPU: {ok_c}")
+        ok = ok and ok_c
+        del bg
     # config 4, single pass: ONE long utterance, its attention windows sharded over the ranks (launcher.encode_long_sharded)
     from qwen3_asr_mlx_b200 import log_mel_spectrogram
 
@@ -56,7 +72,9 @@ def main():
     pg2 = launcher.PeerGather(int(whole.shape[0]) + 8, cfg.output_dim, dtype=torch.float32)
     sharded_nccl = launcher.encode_long_sharded(enc, mel, rank, world)
     sharded_p2p = launcher.encode_long_sharded(enc, mel, rank, world, peer_gather=pg2)
-    ok_long = bool(torch.equal(sharded_nccl, whole)) and bool(torch.equal(sharded_p2p, whole))
+    bg2 = launcher.PeerBlockGather(int(whole.shape[0]) + 8, cfg.output_dim, dtype=torch.float32)
+    sharded_dma = launcher.encode_long_sharded(enc, mel, rank, world, peer_gather=bg2)
+    ok_long = bool(torch.equal(sharded_nccl, whole)) and bool(torch.equal(sharded_p2p, whole)) and bool(torch.equal(sharded_dma, whole))
     if rank == 0:
         print(f"config 4 single pass: {int(whole.shape[0])} tokens, window shares {launcher.window_shares(int(mel.shape[1]), world)}, "
               f"sharded == single-GPU: {ok_long}")
