@@ -7,7 +7,7 @@ Drop-in for that path of gabrimatic/qwen3-asr-mlx: the names exported here are t
 
 __version__ = "0.1.0"
 
-from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch
+from .audio import load_audio, log_mel_spectrogram, log_mel_spectrogram_batch, log_mel_spectrogram_packed
 from .config import AudioEncoderConfig, ModelConfig, TextDecoderConfig
 from .decoder import KVCache, TextDecoder, load_decoder_weights
 from .encoder import AudioEncoder, SinusoidalPositionEmbedding, load_encoder_weights
@@ -21,6 +21,7 @@ __all__ = [
     "load_audio",
     "log_mel_spectrogram",
     "log_mel_spectrogram_batch",
+    "log_mel_spectrogram_packed",
     "AudioEncoderConfig",
     "TextDecoderConfig",
     "ModelConfig",

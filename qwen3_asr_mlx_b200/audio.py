@@ -210,6 +210,30 @@ def log_mel_spectrogram_batch(audios: Sequence, device: Optional[int] = None) ->
     return DeviceArray(mel), foffs
 
 
+def log_mel_spectrogram_packed(packed_audio: torch.Tensor, sample_offsets) -> Tuple[DeviceArray, np.ndarray]:
+    """Log-mel features of a varlen-packed batch that is already resident on the device: ``packed_audio`` is a contiguous 1-D
+    float32 CUDA tensor, utterance ``u`` = ``[sample_offsets[u], sample_offsets[u+1])`` (the layout ``qasr_mel`` takes).  No
+    per-utterance host work beyond the offset arithmetic inside the library; returns ``(mel, frame_offsets)`` as
+    ``log_mel_spectrogram_batch`` does."""
+    if not isinstance(packed_audio, torch.Tensor) or not packed_audio.is_cuda or packed_audio.dtype != torch.float32 \
+            or packed_audio.ndim != 1 or not packed_audio.is_contiguous():
+        raise ValueError("packed_audio must be a contiguous 1-D float32 CUDA tensor")
+    soffs = np.ascontiguousarray(np.asarray(sample_offsets, dtype=np.int64))
+    if soffs.ndim != 1 or len(soffs) < 2 or soffs[0] != 0 or int(soffs[-1]) != packed_audio.numel():
+        raise ValueError("sample_offsets must start at 0 and end at the number of samples")
+    lengths = np.diff(soffs)
+    if (lengths < HOP_LENGTH).any():
+        raise ValueError(f"zero-size array to reduction operation maximum which has no identity (an utterance has < {HOP_LENGTH} samples)")
+    h = runtime.frontend_handle(packed_audio.device.index)
+    foffs = np.zeros(len(soffs), dtype=np.int64)
+    np.cumsum(lengths // HOP_LENGTH, out=foffs[1:])
+    with torch.cuda.device(h.torch_device):
+        mel = torch.empty(int(foffs[-1]) * N_MELS, dtype=torch.float32, device=h.torch_device)
+        h.check(h.lib.qasr_mel(h.ptr, ctypes.c_void_p(packed_audio.data_ptr()), runtime.i64_ptr(soffs), len(soffs) - 1,
+                               ctypes.c_void_p(mel.data_ptr()), h.stream_ptr()))
+    return DeviceArray(mel), foffs
+
+
 def log_mel_spectrogram(audio, n_fft: int = N_FFT, hop_length: int = HOP_LENGTH, n_mels: int = N_MELS,
                         sample_rate: int = SAMPLE_RATE, f_min: float = F_MIN, f_max: float = F_MAX) -> DeviceArray:
     """Log-mel spectrogram of one utterance, shape ``(n_mels, n_samples // 160)`` float32 on the GPU.

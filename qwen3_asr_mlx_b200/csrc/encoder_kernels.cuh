@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "math.cuh"
+#include "mel.cuh"  // ordered_to_float: the per-utterance log-mel maximum is kept as an ordered uint (atomicMax)
 #include "ptx.cuh"
 
 namespace qasr {
@@ -21,7 +22,17 @@ struct ChunkDesc {
   long long mel_base;  // float offset of this utterance's (128, T) block in the packed mel buffer
   int T;               // frames in the utterance
   int frame0;          // first frame of this chunk
+  int utt;             // utterance index within the call (selects the per-utterance log-mel maximum on the fused path)
+  int pad_;
 };
+
+// Fused waveform -> embeddings path: the mel buffer holds the RAW log10 mel (pass 1 of mel.cuh) and the clamp / rescale of
+// audio.py:275-276, max(x, utt_max - 8) then (x + 4) / 4, is applied here while conv1 stages its input -- the utterance
+// maximum is final once pass 1 has ended -- so the normalise pass and its read + write of the whole mel never happen.
+// Same expression as mel_normalize_kernel (bit-identical); a NaN maximum poisons the utterance, like there.
+__device__ __forceinline__ float mel_clamp_rescale(float v, float thr) {
+  return (thr != thr) ? thr : (fmaxf(v, thr) + 4.0f) * 0.25f;
+}
 
 constexpr int kConv1Threads = 240;    // 60 channel groups (8 ch) x 4 pixel slots (C = 480)
 constexpr int kConv1RowsPerCta = 8;   // output rows per CTA  (64 / 8 = 8 CTAs per chunk)
@@ -32,7 +43,7 @@ template <int C>
 __global__ void __launch_bounds__(kConv1Threads)
 conv1_gelu_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ chunks, int chunk0,
                   const float* __restrict__ w /*[C][9]*/, const float* __restrict__ bias /*[C]*/,
-                  __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+                  __nv_bfloat16* __restrict__ planes, long long plane_stride, const unsigned* __restrict__ utt_max) {
   static_assert(C % 8 == 0 && (C / 8) * 4 == kConv1Threads, "thread mapping assumes C == 480");
   constexpr int IW = 104;  // smem row pitch
   __shared__ float in[2 * kConv1RowsPerCta + 1][IW];
@@ -43,13 +54,18 @@ conv1_gelu_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ c
   const ChunkDesc cd = chunks[chunk0 + b];
   const float* __restrict__ src = mel + cd.mel_base;
   const int valid_w = min(100, cd.T - cd.frame0);
+  const bool raw_mel = utt_max != nullptr;
+  const float thr = raw_mel ? ordered_to_float(__ldg(utt_max + cd.utt)) - 8.0f : 0.0f;
 
   // stage input rows h = 2*oh0-1 .. 2*oh0+15, columns w = -1 .. 100 (zero outside the chunk / utterance)
   for (int i = threadIdx.x; i < (2 * kConv1RowsPerCta + 1) * 102; i += kConv1Threads) {
     const int r = i / 102, c = i - r * 102;
     const int h = 2 * oh0 - 1 + r, wv = c - 1;
     float v = 0.0f;
-    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) {
+      v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+      if (raw_mel) v = mel_clamp_rescale(v, thr);
+    }
     in[r][c] = v;
   }
 
@@ -204,7 +220,7 @@ template <int C>
 __global__ void __launch_bounds__(kConv1TcThreads, kConv1TcMinCtas)
 conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ chunks, int chunk0,
                      const __nv_bfloat16* __restrict__ w /*[C][9] bf16*/, const float* __restrict__ bias /*[C]*/,
-                     __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+                     __nv_bfloat16* __restrict__ planes, long long plane_stride, const unsigned* __restrict__ utt_max) {
   static_assert(C == 96 * kConv1TcWarps, "warp/channel mapping assumes C == 480");
   constexpr int IW = 104;
   __shared__ float in[2 * kConv1RowsPerCta + 1][IW];
@@ -215,11 +231,16 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
   const ChunkDesc cd = chunks[chunk0 + b];
   const float* __restrict__ src = mel + cd.mel_base;
   const int valid_w = min(100, cd.T - cd.frame0);
+  const bool raw_mel = utt_max != nullptr;
+  const float thr = raw_mel ? ordered_to_float(__ldg(utt_max + cd.utt)) - 8.0f : 0.0f;
   for (int i = threadIdx.x; i < (2 * kConv1RowsPerCta + 1) * 102; i += kConv1TcThreads) {
     const int r = i / 102, c = i - r * 102;
     const int h = 2 * oh0 - 1 + r, wv = c - 1;
     float v = 0.0f;
-    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+    if (h >= 0 && h < 128 && wv >= 0 && wv < valid_w) {
+      v = __ldg(src + static_cast<long long>(h) * cd.T + cd.frame0 + wv);
+      if (raw_mel) v = mel_clamp_rescale(v, thr);
+    }
     in[r][c] = v;
   }
 

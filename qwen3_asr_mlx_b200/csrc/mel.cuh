@@ -118,9 +118,14 @@ __device__ __forceinline__ int upper_segment(const T* __restrict__ offs, int B, 
   return lo;
 }
 
+// Sample j of the tile's span lives at raw[j + j / 160]: one pad word per hop, so that the 32 frames of a tile (one per lane,
+// 160 samples apart = bank stride 0) read their n-th sample from 32 different banks (stride 161).
+constexpr int kMelRawPadded = (kMelFramesPerCta - 1) * (kMelHop + 1) + kMelNfft + kMelNfft / kMelHop + 1;  // 5394
+static_assert(kMelFramesPerCta == 32 && kMelThreads == 288, "steps A / C / D map the 32 frames of a tile onto the 32 lanes of a warp");
+
 struct MelSmem {
   union {  // the raw samples are dead once step A has produced Y; the power spectrum is written in step C
-    float raw[(kMelFramesPerCta - 1) * kMelHop + kMelNfft];  // 5360
+    float raw[kMelRawPadded];
     float P[kMelFreqs][kMelFramesPerCta + 1];
   };
   float window[kMelNfft];
@@ -161,14 +166,17 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i + u * kMelThreads);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) s.raw[i + u * kMelThreads] = v[u];
+      for (int u = 0; u < 8; ++u) {
+        const int j = i + u * kMelThreads;
+        s.raw[j + j / kMelHop] = v[u];
+      }
     }
-    for (; i < span; i += kMelThreads) s.raw[i] = __ldg(src + i);
+    for (; i < span; i += kMelThreads) s.raw[i + i / kMelHop] = __ldg(src + i);
   } else {
     for (int i = tid; i < span; i += kMelThreads) {
       long long j = first + i;
       if (j < 0 || j >= N) j = reflect_index(j, N);
-      s.raw[i] = __ldg(x + j);
+      s.raw[i + i / kMelHop] = __ldg(x + j);
     }
   }
   for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
@@ -180,26 +188,34 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   }
   __syncthreads();
 
-  // ---- step A/B: 25 real 16-point DFTs per frame, twiddled
-  for (int task = tid; task < nf * 25; task += kMelThreads) {
-    const int f = task / 25, n2 = task - f * 25;
-    const float* fr = s.raw + f * kMelHop + n2;
-    float v[16];
+  // Every step maps the tile's frames onto lanes (lane = frame) and one unit of work onto a warp, so that table lookups
+  // (window, twiddles, filter taps) are warp-uniform broadcasts, branches are uniform and every shared-memory access of a
+  // warp hits 32 different banks (ncu on the previous task-major mapping: 30 % of the LSU wavefronts were bank conflicts).
+  const int lane = tid & 31, warp = tid >> 5;
+  // ---- step A/B: 25 real 16-point DFTs per frame, twiddled; warp = input residue n2 (3 rounds of 9 warps)
+  for (int n2 = warp; n2 < 25; n2 += kMelThreads / 32) {
+    if (lane < nf) {
+      const float* fr = s.raw + lane * (kMelHop + 1);
+      float v[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = fr[25 * n1] * s.window[25 * n1 + n2];
-    fft::cf y[9];
-    fft::rdft16(v, y);
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int j = 25 * n1 + n2;                                   // sample within the frame (warp-uniform)
+        v[n1] = fr[j + (j >= kMelHop) + (j >= 2 * kMelHop)] * s.window[j];
+      }
+      fft::cf y[9];
+      fft::rdft16(v, y);
 #pragma unroll
-    for (int k1 = 0; k1 < 9; ++k1) {
-      const float2 w = s.twiddle[k1 * 25 + n2];
-      s.Y[f][k1][n2] = make_float2(y[k1].re * w.x - y[k1].im * w.y, y[k1].re * w.y + y[k1].im * w.x);
+      for (int k1 = 0; k1 < 9; ++k1) {
+        const float2 w = s.twiddle[k1 * 25 + n2];
+        s.Y[lane][k1][n2] = make_float2(y[k1].re * w.x - y[k1].im * w.y, y[k1].re * w.y + y[k1].im * w.x);
+      }
     }
   }
   __syncthreads();
 
-  // ---- step C: 9 complex 25-point DFTs per frame -> power spectrum P[bin][frame]
-  for (int task = tid; task < nf * 9; task += kMelThreads) {
-    const int f = task / 9, k1 = task - f * 9;
+  // ---- step C: 9 complex 25-point DFTs per frame -> power spectrum P[bin][frame]; warp = k1 (one round)
+  if (lane < nf) {
+    const int f = lane, k1 = warp;
     fft::cf z[25];
 #pragma unroll
     for (int i = 0; i < 25; ++i) {

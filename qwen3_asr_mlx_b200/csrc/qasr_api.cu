@@ -100,6 +100,7 @@ struct qasr_handle {
   bool attn_tc = true;      // QASR_ATTN_TC=0 selects the mma.sync attention kernel instead of the tcgen05 one
   bool cta_pair = true;     // QASR_CTA_PAIR=0 selects the single-CTA (cta_group::1) GEMM kernels
   bool small_tiles = true;     // QASR_SMALL_TILES=0 keeps the 256-wide tiles for small batches too
+  bool mel_one_pass = true;    // QASR_MEL_ONE_PASS=0 runs mel_normalize_kernel on the fused path too (A/B testing; bit-identical)
   bool conv_tail_skip = true;  // QASR_CONV_TAIL_SKIP=0 issues the MMAs over the zero-filled half of a tap's last K block too
   qasr_stats stats{};
 
@@ -502,8 +503,10 @@ int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, 
   return QASR_OK;
 }
 
+// normalize = false leaves the RAW log10 mel in mel_dev and the per-utterance maxima in h->d_uttmax: the fused entry point
+// lets conv1 apply the clamp / rescale while it stages its input (one pass over the mel instead of two).
 int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int B, float* mel_dev,
-             std::vector<long long>* frame_offsets_out, cudaStream_t st) {
+             std::vector<long long>* frame_offsets_out, cudaStream_t st, bool normalize = true) {
   if (!audio_dev || !sample_offsets || !mel_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_mel: bad argument");
   std::vector<long long> soffs(B + 1), foffs(B + 1);
   std::vector<int> boffs(B + 1);
@@ -547,7 +550,7 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
   QCUDA(h, cudaGetLastError());
   const long long total_vec4 = foffs[B] * (kMelBins / 4);
   const long long nblk = (total_vec4 + kMelNormVecPerCta - 1) / kMelNormVecPerCta;
-  {
+  if (normalize) {
     ProfScope ps(h, QASR_PROF_MEL_NORM, st, 0.0, 8.0 * kMelBins * foffs[B]);
     mel_normalize_kernel<<<static_cast<unsigned>(nblk), kMelNormThreads, 0, st>>>(
         mel_dev, static_cast<const long long*>(h->d_foffs.p), B, static_cast<const unsigned*>(h->d_uttmax.p), total_vec4);
@@ -561,7 +564,7 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
 // a lane's share starts in the middle of the packed mel buffer), on one lane's workspace and one stream.
 // toffs (B + 1 entries, relative to the share's first token) is filled in.
 int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
-                int out_dtype, long long* toffs, cudaStream_t st) {
+                int out_dtype, long long* toffs, cudaStream_t st, const unsigned* utt_max = nullptr, int utt_base = 0) {
   const qasr_config& c = h->cfg;
   const int D = c.d_model, F = c.encoder_ffn_dim, H = c.encoder_attention_heads;
   const int wtok = window_tokens(c);
@@ -579,7 +582,7 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
     for (long long f0 = 0; f0 < T; f0 += kChunkFrames) {
       const int real = static_cast<int>(T - f0 < kChunkFrames ? T - f0 : kChunkFrames);
       const int valid = conv_len3(real);
-      chunks.push_back(ChunkDesc{static_cast<long long>(kMelBins) * frame_offsets[u], static_cast<int>(T), static_cast<int>(f0)});
+      chunks.push_back(ChunkDesc{static_cast<long long>(kMelBins) * frame_offsets[u], static_cast<int>(T), static_cast<int>(f0), utt_base + u, 0});
       for (int t = 0; t < kTokensPerChunk; ++t) rowmap.push_back(t < valid ? static_cast<int>(tok + t) : -1);
       tok += valid;
     }
@@ -620,11 +623,11 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
       if (h->conv1_fp32)
         conv1_gelu_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1Threads, 0, st>>>(
             mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
-            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1);
+            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1, utt_max);
       else
         conv1_gelu_tc_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1TcThreads, 0, st>>>(
             mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
-            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1);
+            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1, utt_max);
     }
     QCUDA(h, cudaGetLastError());
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
@@ -718,7 +721,7 @@ long long chunks_of(long long frames) { return (frames + kChunkFrames - 1) / kCh
 // Utterances are independent (the reference loops over them one at a time, model.py:239), so the split
 // changes no result; it is made at the utterance boundary that balances the 100-frame chunk counts.
 int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
-                int out_dtype, int64_t* token_offsets_out, cudaStream_t st) {
+                int out_dtype, int64_t* token_offsets_out, cudaStream_t st, const unsigned* utt_max = nullptr) {
   if (!h->finalized) return fail(h, QASR_ERR_STATE, "weights not finalised (call qasr_finalize_weights)");
   if (!mel_dev || !frame_offsets || !emb_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
   if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
@@ -740,7 +743,7 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
   std::vector<long long> toffs(B + 2, 0);
   int rc;
   if (split >= B) {
-    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, B, emb_dev, out_dtype, toffs.data(), st))) return rc;
+    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, B, emb_dev, out_dtype, toffs.data(), st, utt_max, 0))) return rc;
   } else {
     // Profiling brackets every launch with events on ONE stream: the lanes then run back to back on `st`.
     cudaStream_t st1 = h->profile ? st : h->lane_stream;
@@ -749,10 +752,10 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
       QCUDA(h, cudaStreamWaitEvent(st1, h->ev_fork, 0));
     }
     std::vector<long long> t0(split + 1), t1(B - split + 1);
-    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, split, emb_dev, out_dtype, t0.data(), st))) return rc;
+    if ((rc = encode_lane(h, h->lanes[0], mel_dev, frame_offsets, split, emb_dev, out_dtype, t0.data(), st, utt_max, 0))) return rc;
     const size_t esz = out_dtype == QASR_BF16 ? 2 : 4;
     void* emb1 = static_cast<uint8_t*>(emb_dev) + static_cast<size_t>(t0[split]) * h->cfg.output_dim * esz;
-    if ((rc = encode_lane(h, h->lanes[1], mel_dev, frame_offsets + split, B - split, emb1, out_dtype, t1.data(), st1))) return rc;
+    if ((rc = encode_lane(h, h->lanes[1], mel_dev, frame_offsets + split, B - split, emb1, out_dtype, t1.data(), st1, utt_max, split))) return rc;
     if (!h->profile) {
       QCUDA(h, cudaEventRecord(h->ev_join, st1));
       QCUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -812,6 +815,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
     if (v > 0) h->stem_group = v;
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
+  if (const char* mo = getenv("QASR_MEL_ONE_PASS")) h->mel_one_pass = atoi(mo) != 0;
   if (const char* ls = getenv("QASR_LANES")) h->two_lanes = atoi(ls) >= 2;
   if (const char* lm = getenv("QASR_LANE_MIN_CHUNKS")) h->lane_min_chunks = atoll(lm);
   if (cudaEventCreateWithFlags(&h->pin_event, cudaEventDisableTiming) != cudaSuccess ||
@@ -1083,8 +1087,11 @@ int call_body(qasr_handle* h, const CallArgs& c, cudaStream_t st) {
     return encode_impl(h, c.in, fo.data(), c.B, c.out, c.out_dtype, c.toffs_out, st);
   }
   std::vector<long long> foffs;
-  if ((rc = mel_impl(h, c.in, c.offs, c.B, static_cast<float*>(h->mel_scratch.p), &foffs, st))) return rc;
-  return encode_impl(h, static_cast<const float*>(h->mel_scratch.p), foffs.data(), c.B, c.out, c.out_dtype, c.toffs_out, st);
+  // fused path: ONE pass over the mel -- the scratch keeps the raw log10 mel, conv1 applies max(x, utt_max - 8), (x + 4) / 4
+  const bool one_pass = h->mel_one_pass;
+  if ((rc = mel_impl(h, c.in, c.offs, c.B, static_cast<float*>(h->mel_scratch.p), &foffs, st, !one_pass))) return rc;
+  return encode_impl(h, static_cast<const float*>(h->mel_scratch.p), foffs.data(), c.B, c.out, c.out_dtype, c.toffs_out, st,
+                     one_pass ? static_cast<const unsigned*>(h->d_uttmax.p) : nullptr);
 }
 
 // Upper bound of the pinned table bytes one call needs, plus scratch sizing for the fused entry.

@@ -460,3 +460,38 @@ def test_weight_shapes_are_validated(small):
         with pytest.raises(ValueError):
             enc.load_weights(p)
         enc.close()
+
+
+def test_one_pass_mel_on_the_fused_path_is_bit_identical(small, monkeypatch):
+    """Waveform -> embeddings: the mel scratch keeps the raw log10 mel and conv1 applies max(x, utt_max - 8), (x + 4) / 4
+    while staging its input (no normalise pass).  Bit-identical to (a) the two-pass variant and (b) mel followed by encoder
+    through the separate entry points, for ragged batches including a NaN utterance and a two-lane split."""
+    from qwen3_asr_mlx_b200 import AudioEncoder, log_mel_spectrogram_batch
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(5)
+    xs = [synth(rng, int(n)) for n in (160, 16000 * 3 + 77, 16000 * 12, 4000, 16000 * 9 + 4321)]
+    xs[3] = (xs[3] * 1e-4).astype(np.float32)                     # a quiet utterance: clamp floor well above most bins
+    fused = np.array(enc.encode_audio_batch(xs)[0])
+    mel, foffs = log_mel_spectrogram_batch(xs)
+    mels = [mel.tensor[128 * int(a): 128 * int(b)].view(128, -1) for a, b in zip(foffs[:-1], foffs[1:])]
+    separate = np.array(enc.encode_batch(mels)[0])
+    assert np.array_equal(fused, separate)
+    monkeypatch.setenv("QASR_MEL_ONE_PASS", "0")
+    two_pass = AudioEncoder(cfg)
+    two_pass.load_weights(params)
+    assert np.array_equal(np.array(two_pass.encode_audio_batch(xs)[0]), fused)
+    l_two = two_pass.stats()["kernel_launches"]
+    two_pass.encode_audio_batch(xs)
+    l_two = two_pass.stats()["kernel_launches"] - l_two
+    two_pass.close()
+    l_one = enc.stats()["kernel_launches"]
+    enc.encode_audio_batch(xs)
+    assert enc.stats()["kernel_launches"] - l_one == l_two - 1   # the normalise launch is gone
+    monkeypatch.delenv("QASR_MEL_ONE_PASS")
+    monkeypatch.setenv("QASR_LANES", "2")
+    monkeypatch.setenv("QASR_LANE_MIN_CHUNKS", "1")
+    lanes = AudioEncoder(cfg)
+    lanes.load_weights(params)
+    assert np.array_equal(np.array(lanes.encode_audio_batch(xs)[0]), fused)   # lane 1 indexes the maxima with its utterance base
+    lanes.close()
