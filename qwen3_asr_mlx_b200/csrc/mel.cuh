@@ -234,21 +234,27 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   }
   __syncthreads();
 
-  // ---- banded mel filterbank + log10, frame index fastest (coalesced 128-byte rows)
+  // ---- banded mel filterbank + log10; warp = mel bin (15 rounds of 9 warps), lane = frame (coalesced 128-byte rows).
+  // All taps of a bin are loaded before the FMA chain starts (the tap count is warp-uniform), so a round costs one
+  // shared-memory latency instead of one per tap; the summation order is unchanged.
   float lmax = -INFINITY;
   float* __restrict__ out = mel_out + f0 * kMelBins;
-  for (int task = tid; task < kMelBins * kMelFramesPerCta; task += kMelThreads) {
-    const int m = task / kMelFramesPerCta, f = task - m * kMelFramesPerCta;
-    if (f < nf) {
-      const int st = s.fb_start[m], cnt = s.fb_count[m];  // warp-uniform (one mel bin per warp pass)
+  for (int m = warp; m < kMelBins; m += kMelThreads / 32) {
+    if (lane < nf) {
+      const int st = s.fb_start[m], cnt = s.fb_count[m];
       const float* w = s.fb_weight + m * kMelMaxTaps;
+      float pv[kMelMaxTaps];
+#pragma unroll
+      for (int j = 0; j < kMelMaxTaps; ++j) pv[j] = (j < cnt) ? s.P[st + j][lane] : 0.0f;
       float acc = 0.0f;
-      for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], s.P[st + j][f], acc);
+#pragma unroll
+      for (int j = 0; j < kMelMaxTaps; ++j)
+        if (j < cnt) acc = fmaf(w[j], pv[j], acc);
       // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here.
       // A non-finite sample makes its frames NaN in the reference (np.maximum / .max() propagate NaN, audio.py:274-275)
       // and, through the utterance-wide max, the whole utterance: NaN is carried, not dropped by fmaxf.
       const float v = (acc != acc) ? kMelNaN : __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
-      out[static_cast<long long>(m) * T + t0 + f] = v;
+      out[static_cast<long long>(m) * T + t0 + lane] = v;
       lmax = nan_max(lmax, v);
     }
   }
