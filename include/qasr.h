@@ -107,7 +107,8 @@ int qasr_count_tokens(const qasr_handle* h, int64_t n_frames, int64_t* n_tokens)
 /* Optional: pre-size the workspace so that later calls with total_frames <= this allocate nothing. */
 int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch);
 
-/* ---- device-pointer entry points (inputs/outputs resident in HBM; offsets are HOST arrays) ---- */
+/* ---- device-pointer entry points (inputs/outputs resident in HBM; offsets are HOST arrays) ----
+ * emb_dev / mel_dev must be 16-byte aligned (the epilogues store tiles through TMA); cudaMalloc'd buffers always are. */
 int qasr_mel(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch, float* mel_dev,
              void* stream);
 int qasr_encode(qasr_handle* h, const float* mel_dev, const int64_t* frame_offsets, int32_t batch, void* emb_dev,
@@ -189,6 +190,10 @@ int qasr_debug_read(qasr_handle* h, const char* what, float* host_out, size_t n_
  * a/w bf16 HOST arrays, out fp32 HOST array.  mode: 0 store, 1 gelu, 2 residual (out += result, out is also an input); +16 selects the CTA-pair (cta_group::2) kernel. */
 int qasr_test_gemm(int device, const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, int32_t M,
                    int32_t N, int32_t K, int32_t mode, float* out);
+
+/* The GELU the epilogues evaluate (math.cuh gelu_from_half, applied to x / 2 like the kernels do), elementwise on a HOST array:
+ * lets a test bound its deviation from the reference's exact-erf nn.gelu (encoder.py:118,273-275,320) over every bf16 input. */
+int qasr_test_gelu(int device, const float* x_host, int32_t n, float* out_host);
 
 /* Micro-benchmark of the dense tcgen05 GEMM on device-resident pseudo-random bf16 operands (CUDA-event timed, back to back).
  * mode: 0 bf16 store, 1 bias+GELU bf16 store, 2 fp32 residual (TMA reduce-add), 3 accumulators discarded (main-loop ceiling);

@@ -106,6 +106,7 @@ _SIGNATURES = {
     "qasr_decoder_prefill": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qasr_decoder_get_stats": (c_int, [c_void_p, POINTER(QasrStats)]),
     "qasr_bench_gemm": (c_int, [c_int, c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
+    "qasr_test_gelu": (c_int, [c_int, POINTER(c_float), c_int32, POINTER(c_float)]),
     "qasr_test_gemm": (c_int, [c_int, POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int32, c_int32, c_int32, c_int32, POINTER(c_float)]),
 }
 

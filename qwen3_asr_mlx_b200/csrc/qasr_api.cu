@@ -1664,6 +1664,29 @@ int qasr_bench_gemm(int device, int32_t M, int32_t N, int32_t K, int32_t mode, i
   return QASR_OK;
 }
 
+namespace {
+__global__ void test_gelu_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gelu_from_half(0.5f * x[i]);  // the epilogues see h = x / 2 (weights and bias pre-scaled by 0.5)
+}
+}  // namespace
+
+int qasr_test_gelu(int device, const float* x, int32_t n, float* out) {
+  if (!x || !out || n <= 0) return fail(nullptr, QASR_ERR_INVALID, "qasr_test_gelu: bad argument");
+  qasr_handle* h = nullptr;
+  QCUDA(h, cudaSetDevice(device));
+  float *dx = nullptr, *dout = nullptr;
+  QCUDA(h, cudaMalloc(&dx, static_cast<size_t>(n) * 4));
+  QCUDA(h, cudaMalloc(&dout, static_cast<size_t>(n) * 4));
+  QCUDA(h, cudaMemcpy(dx, x, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice));
+  test_gelu_kernel<<<(n + 255) / 256, 256>>>(dx, n, dout);
+  QCUDA(h, cudaGetLastError());
+  QCUDA(h, cudaMemcpy(out, dout, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dx);
+  cudaFree(dout);
+  return QASR_OK;
+}
+
 int qasr_test_gemm(int device, const uint16_t* a, const uint16_t* w, const float* bias, int32_t M, int32_t N, int32_t K,
                    int32_t mode, float* out) {
   if (!a || !w || !out || M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0)

@@ -192,8 +192,8 @@ class AudioEncoder:
         tdt, cdt = (torch.bfloat16, _lib.QASR_BF16) if out_dtype in ("bfloat16", "bf16") else (torch.float32, _lib.QASR_F32)
         if out is None:
             out = torch.empty((n_tok, self.config.output_dim), dtype=tdt, device=h.torch_device)
-        elif tuple(out.shape) != (n_tok, self.config.output_dim) or out.dtype != tdt or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous {tdt} tensor of shape {(n_tok, self.config.output_dim)}")
+        elif tuple(out.shape) != (n_tok, self.config.output_dim) or out.dtype != tdt or not out.is_contiguous() or out.data_ptr() % 16:
+            raise ValueError(f"out must be a contiguous, 16-byte aligned {tdt} tensor of shape {(n_tok, self.config.output_dim)}")
         toffs = np.zeros(B + 1, dtype=np.int64)
         h.check(h.lib.qasr_encode_audio(h.ptr, ctypes.c_void_p(packed_audio.data_ptr()), runtime.i64_ptr(soffs), B,
                                         ctypes.c_void_p(out.data_ptr()), cdt, runtime.i64_ptr(toffs), h.stream_ptr()))

@@ -316,7 +316,11 @@ def encode_contiguous_sharded(encoder, packed_audio: torch.Tensor, n_samples: Se
     else:
         local = torch.empty((my_rows, encoder.config.output_dim), dtype=tdt, device=packed_audio.device)
     sample_pos, row_pos = 0, 0
-    for sub in split_by_budget(mine, costs, tokens_per_call):
+    # as many sub-batches as the budget requires, but of EQUAL size: no tiny tail call, and the last (exposed) push is 1/n
+    n_sub = max(1, -(-my_rows // max(1, int(tokens_per_call))))
+    even = -(-my_rows // n_sub) if my_rows else tokens_per_call
+    longest = max((costs[i] for i in mine), default=0)
+    for sub in split_by_budget(mine, costs, min(int(tokens_per_call), even + longest)):
         so = np.zeros(len(sub) + 1, dtype=np.int64)
         np.cumsum([int(n_samples[i]) for i in sub], out=so[1:])
         rows = sum(costs[i] for i in sub)
