@@ -333,9 +333,15 @@ def measure_sharded_configs(enc, cfg, rank, world, reps=3):
         if gather is not None:
             ms, (emb, offs, _) = _timed_max(full, world, 1)
             all_ms.append(ms)
-    ms_gather_alone = None
+    ms_gather_alone, trace = None, None
     if gather is not None:
         finite = bool(torch.isfinite(emb[::997].float()).all().item())
+        if os.environ.get("QASR_GATHER_TRACE"):  # one traced pass: when was each block produced / pushed, on this rank
+            gather.trace = []
+            _timed_max(full, world, 1)
+            t0 = gather.trace[0][1]
+            trace = [(label, round(t0.elapsed_time(ev), 3)) for label, ev in gather.trace]
+            gather.trace = None
 
         def gather_alone():  # the same transfers with no compute to hide behind: begin barrier, all block pushes, finish barrier
             gather.begin()
@@ -353,7 +359,7 @@ def measure_sharded_configs(enc, cfg, rank, world, reps=3):
         "utterances": len(lengths), "audio_seconds": audio_s, "tokens": total, "tokens_per_rank_min_max": [min(per_rank), max(per_rank)],
         "partition": "contiguous token-balanced shares (launcher.contiguous_partition)", "sub_batch_tokens": 32768,
         "forward_ms": ms_fwd, "with_gather_ms": ms_all, "gather_exposed_ms": ms_all - ms_fwd, "first_gather_ms": ms_cold,
-        "forward_ms_passes": fwd_ms, "with_gather_ms_passes": all_ms, "gather_alone_ms": ms_gather_alone,
+        "forward_ms_passes": fwd_ms, "with_gather_ms_passes": all_ms, "gather_alone_ms": ms_gather_alone, "trace_rank0_ms": trace,
         "gather_overhead_frac": (ms_all - ms_fwd) / ms_fwd,
         "audio_s_per_s_forward": audio_s / (ms_fwd / 1e3), "audio_s_per_s_with_gather": audio_s / (ms_all / 1e3),
         "nvlink_bytes_pushed_per_rank": (gather.bytes_pushed // (reps + 1)) if gather is not None else 0,

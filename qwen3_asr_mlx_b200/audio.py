@@ -162,8 +162,8 @@ def pack_waveforms(h, waves: Sequence) -> Tuple[torch.Tensor, np.ndarray]:
     host loop of device copies: host arrays are concatenated on the host and uploaded with one H2D copy; device tensors that
     already lie back to back in one allocation are used in place (zero copy); any other set of device tensors goes through
     ``qasr_pack_audio`` (one pointer-table upload + one kernel, whatever the batch size)."""
-    lengths = [int(w.shape[0]) for w in waves]
-    soffs = runtime.offsets_array(lengths)
+    soffs = np.zeros(len(waves) + 1, dtype=np.int64)
+    np.cumsum(np.fromiter((w.shape[0] for w in waves), dtype=np.int64, count=len(waves)), out=soffs[1:])
     dev = h.torch_device
     if len(waves) == 1:
         return as_device_f32(waves[0], dev), soffs
@@ -173,12 +173,15 @@ def pack_waveforms(h, waves: Sequence) -> Tuple[torch.Tensor, np.ndarray]:
     tens = [w if (isinstance(w, torch.Tensor) and w.device == dev and w.dtype == torch.float32 and w.is_contiguous())
             else as_device_f32(w, dev) for w in waves]
     base = tens[0]
-    adjacent = all(t.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() for t in tens) and all(
-        tens[i + 1].data_ptr() == tens[i].data_ptr() + 4 * lengths[i] for i in range(len(tens) - 1))
+    addr = np.fromiter((t.data_ptr() for t in tens), dtype=np.int64, count=len(tens))
+    # back to back AND inside the first tensor's allocation (no other allocation can lie inside its address range)
+    st = base.untyped_storage()
+    adjacent = bool(np.array_equal(addr[1:], addr[:-1] + 4 * soffs[1:-1] - 4 * soffs[:-2])) and \
+        st.data_ptr() <= int(addr[0]) and int(addr[0]) + 4 * int(soffs[-1]) <= st.data_ptr() + st.nbytes()
     if adjacent:
         return torch.as_strided(base, (int(soffs[-1]),), (1,)), soffs
     packed = torch.empty(int(soffs[-1]), dtype=torch.float32, device=dev)
-    ptrs = (ctypes.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+    ptrs = (ctypes.c_void_p * len(tens)).from_buffer(addr.astype(np.uint64))
     h.check(h.lib.qasr_pack_audio(h.ptr, ptrs, runtime.i64_ptr(soffs), len(tens), ctypes.c_void_p(packed.data_ptr()), h.stream_ptr()))
     # the sources must stay alive until the kernel has read them: they are referenced by `tens` until this frame returns and the
     # caching allocator only hands their memory to later work on the same stream
@@ -196,12 +199,12 @@ def log_mel_spectrogram_batch(audios: Sequence, device: Optional[int] = None) ->
     waves = [_as_waveform(a, SAMPLE_RATE) for a in audios]
     if not waves:
         raise ValueError("empty batch")
-    lengths = [int(w.shape[0]) for w in waves]
-    for n in lengths:
-        if n < HOP_LENGTH:
-            # the reference fails here with numpy's "zero-size array to reduction operation maximum"
-            raise ValueError(f"zero-size array to reduction operation maximum which has no identity (audio of {n} samples < {HOP_LENGTH})")
-    foffs = runtime.offsets_array([n // HOP_LENGTH for n in lengths])
+    lengths = np.fromiter((w.shape[0] for w in waves), dtype=np.int64, count=len(waves))
+    if int(lengths.min()) < HOP_LENGTH:
+        # the reference fails here with numpy's "zero-size array to reduction operation maximum"
+        raise ValueError(f"zero-size array to reduction operation maximum which has no identity (audio of {int(lengths.min())} samples < {HOP_LENGTH})")
+    foffs = np.zeros(len(waves) + 1, dtype=np.int64)
+    np.cumsum(lengths // HOP_LENGTH, out=foffs[1:])
     with torch.cuda.device(h.torch_device):
         packed, soffs = pack_waveforms(h, waves)
         mel = torch.empty(int(foffs[-1]) * N_MELS, dtype=torch.float32, device=h.torch_device)

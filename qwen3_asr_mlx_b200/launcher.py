@@ -254,10 +254,19 @@ class PeerBlockGather:
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(n_streams, len(self.peers))))]
         self.bytes_pushed = 0
         self._pending = False
+        self.trace = None  # set to [] to record (label, event) pairs: when each block was produced / had landed at the peers
 
     def begin(self) -> None:
         """Every rank has finished reading the previous result (its buffer may be overwritten)."""
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            self.trace.append(("begin", e))
         self.handle.barrier(channel=0)
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            self.trace.append(("begin barrier passed", e))
 
     def rows(self, row0: int, n: int) -> torch.Tensor:
         return self.buf[row0: row0 + n]
@@ -266,14 +275,21 @@ class PeerBlockGather:
         """Copy rows [row0, row0 + n) of the local buffer (already queued on the current stream) to every peer."""
         if n <= 0 or not self.peers:
             return
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=self.trace is not None)
         ev.record(torch.cuda.current_stream())
+        if self.trace is not None:
+            self.trace.append((f"block@{row0} produced", ev))
         src = self.buf[row0: row0 + n]
         for k, p in enumerate(self.peers):
             st = self.streams[k % len(self.streams)]
             st.wait_event(ev)
             with torch.cuda.stream(st):
                 self.peer_bufs[p][row0: row0 + n].copy_(src, non_blocking=True)
+        if self.trace is not None:
+            for i, st in enumerate(self.streams):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(st)
+                self.trace.append((f"block@{row0} pushed (stream {i})", e))
         self.bytes_pushed += n * self.dim * self.buf.element_size() * len(self.peers)
         self._pending = True
 
@@ -285,7 +301,15 @@ class PeerBlockGather:
                 ev.record(st)
                 cur.wait_event(ev)
             self._pending = False
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(cur)
+            self.trace.append(("local pushes joined", e))
         self.handle.barrier(channel=1)  # every rank's blocks have landed everywhere
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(cur)
+            self.trace.append(("barrier passed", e))
         return self.buf[:total_rows]
 
 
