@@ -123,6 +123,24 @@ __device__ __forceinline__ int upper_segment(const T* __restrict__ offs, int B, 
 constexpr int kMelRawPadded = (kMelFramesPerCta - 1) * (kMelHop + 1) + kMelNfft + kMelNfft / kMelHop + 1;  // 5394
 static_assert(kMelFramesPerCta == 32 && kMelThreads == 288, "steps A / C / D map the 32 frames of a tile onto the 32 lanes of a warp");
 
+// One mel bin of one frame: CNT taps of the banded filter against the power spectrum column of this lane's frame.  The tap
+// count is warp-uniform (warp = mel bin), so the caller dispatches on it with a uniform switch: only the taps that exist
+// are issued (3.1 on average against the 12 predicated slots of the generic loop, which made this step half of the
+// kernel's instructions).  All loads first, then the FMA chain in ascending tap order (same summation order as before).
+template <int CNT>
+__device__ __forceinline__ float mel_band(const float* __restrict__ w, const float* __restrict__ p) {
+  float pv[CNT], wv[CNT];
+#pragma unroll
+  for (int j = 0; j < CNT; ++j) {
+    pv[j] = p[j * (kMelFramesPerCta + 1)];
+    wv[j] = w[j];
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CNT; ++j) acc = fmaf(wv[j], pv[j], acc);
+  return acc;
+}
+
 struct MelSmem {
   union {  // the raw samples are dead once step A has produced Y; the power spectrum is written in step C
     float raw[kMelRawPadded];
@@ -158,20 +176,25 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   const long long first = static_cast<long long>(t0) * kMelHop - kMelNfft / 2;
   const float* __restrict__ x = audio + s0;
   if (first >= 0 && first + span <= N) {
-    // interior tile (the common case): no reflection, 8 independent loads in flight per thread
+    // interior tile (the common case): no reflection.  A warp copies whole hops (160 samples -> 161 padded words), five
+    // coalesced loads in flight per thread and no per-sample index division.
     const float* __restrict__ src = x + first;
-    int i = tid;
-    for (; i + 7 * kMelThreads < span; i += 8 * kMelThreads) {
-      float v[8];
+    for (int hop = tid >> 5; hop * kMelHop < span; hop += kMelThreads / 32) {
+      const float* __restrict__ sp = src + hop * kMelHop;
+      float* __restrict__ dp = s.raw + hop * (kMelHop + 1);
+      const int left = span - hop * kMelHop;
+      float v[kMelHop / 32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i + u * kMelThreads);
+      for (int k = 0; k < kMelHop / 32; ++k) {
+        const int i = (tid & 31) + 32 * k;
+        v[k] = (i < left) ? __ldg(sp + i) : 0.0f;
+      }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = i + u * kMelThreads;
-        s.raw[j + j / kMelHop] = v[u];
+      for (int k = 0; k < kMelHop / 32; ++k) {
+        const int i = (tid & 31) + 32 * k;
+        if (i < left) dp[i] = v[k];
       }
     }
-    for (; i < span; i += kMelThreads) s.raw[i + i / kMelHop] = __ldg(src + i);
   } else {
     for (int i = tid; i < span; i += kMelThreads) {
       long long j = first + i;
@@ -195,12 +218,17 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   // ---- step A/B: 25 real 16-point DFTs per frame, twiddled; warp = input residue n2 (3 rounds of 9 warps)
   for (int n2 = warp; n2 < 25; n2 += kMelThreads / 32) {
     if (lane < nf) {
-      const float* fr = s.raw + lane * (kMelHop + 1);
+      // sample j = 25 n1 + n2 of the frame sits j / 160 pad words further (see kMelRawPadded); only n1 = 6 and n1 = 12
+      // straddle a hop boundary depending on n2, every other offset is a compile-time immediate
+      const float* fr = s.raw + lane * (kMelHop + 1) + n2;
+      const float* wn = s.window + n2;
+      const int p6 = (n2 >= 10) ? 1 : 0, p12 = (n2 >= 20) ? 2 : 1;
+      static_assert(kMelHop == 160 && kMelNfft == 400, "pad offsets below are written out for hop 160, n_fft 400");
       float v[16];
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const int j = 25 * n1 + n2;                                   // sample within the frame (warp-uniform)
-        v[n1] = fr[j + (j >= kMelHop) + (j >= 2 * kMelHop)] * s.window[j];
+        const int pad = (n1 < 6) ? 0 : (n1 == 6) ? p6 : (n1 < 12) ? 1 : (n1 == 12) ? p12 : 2;
+        v[n1] = fr[25 * n1 + pad] * wn[25 * n1];
       }
       fft::cf y[9];
       fft::rdft16(v, y);
@@ -243,13 +271,24 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
     if (lane < nf) {
       const int st = s.fb_start[m], cnt = s.fb_count[m];
       const float* w = s.fb_weight + m * kMelMaxTaps;
-      float pv[kMelMaxTaps];
-#pragma unroll
-      for (int j = 0; j < kMelMaxTaps; ++j) pv[j] = (j < cnt) ? s.P[st + j][lane] : 0.0f;
+      const float* pcol = &s.P[st][lane];
       float acc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < kMelMaxTaps; ++j)
-        if (j < cnt) acc = fmaf(w[j], pv[j], acc);
+      static_assert(kMelMaxTaps == 12, "the dispatch below lists every tap count");
+      switch (cnt) {
+        case 1: acc = mel_band<1>(w, pcol); break;
+        case 2: acc = mel_band<2>(w, pcol); break;
+        case 3: acc = mel_band<3>(w, pcol); break;
+        case 4: acc = mel_band<4>(w, pcol); break;
+        case 5: acc = mel_band<5>(w, pcol); break;
+        case 6: acc = mel_band<6>(w, pcol); break;
+        case 7: acc = mel_band<7>(w, pcol); break;
+        case 8: acc = mel_band<8>(w, pcol); break;
+        case 9: acc = mel_band<9>(w, pcol); break;
+        case 10: acc = mel_band<10>(w, pcol); break;
+        case 11: acc = mel_band<11>(w, pcol); break;
+        case 12: acc = mel_band<12>(w, pcol); break;
+        default: break;
+      }
       // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here.
       // A non-finite sample makes its frames NaN in the reference (np.maximum / .max() propagate NaN, audio.py:274-275)
       // and, through the utterance-wide max, the whole utterance: NaN is carried, not dropped by fmaxf.

@@ -1,6 +1,6 @@
 """Turn the CSV pages of the round-end ncu captures (tests/final_evidence.sh) into the summaries kept under profiles/.
 
-    python tests/summarize_ncu.py gpurun_out profiles r01
+    python tests/summarize_ncu.py gpurun_out profiles r02
 """
 import csv
 import json
@@ -60,18 +60,24 @@ def launch_summary(path, out, title):
 
 
 full_summary(f"{src}/{tag}_step_full2_raw.csv", f"{dst}/{tag}_ncu_full_summary.txt",
-             "# ncu --set full --clock-control none, 17 consecutive launches of the 2nd step of config 2 (mel x2, stem x8 for two chunk groups, then LN, qkv, attention, out_proj, LN, fc1, fc2 of layer 0)")
+             "# ncu --set full --clock-control none, 17 consecutive launches of the 2nd step of config 2 (mel, stem x8 for two chunk groups, then LN, qkv, attention, out_proj, LN, fc1, fc2 of layer 0, LN of layer 1)")
 full_summary(f"{src}/{tag}_prefill_full2_raw.csv", f"{dst}/{tag}_ncu_prefill_summary.txt",
              "# ncu --set full --clock-control none, the 19 launches of one decoder-prefill call (tests/ncu_prefill.py: 2 layers, 1.7B widths, 64 x 407 prompt rows)\n"
              "# gemm_bf16_sm100<256,6,0,EPI,2,0>: EPI 0 = q|k|v (bf16 store), 2 = o_proj / down (fp32 TMA reduce-add), 10 = gate|up SwiGLU, 3 = lm_head (fp32 TMA store)")
-launch_summary(f"{src}/{tag}_launches_final2.csv", f"{dst}/{tag}_ncu_launches_summary.txt",
-               "# ncu launch list of ONE step (config 2: 64 x 30 s, eager launches, 181 kernels) -- gpu__time_duration.sum, --clock-control none\n"
+launch_summary(f"{src}/{tag}_launches_final.csv", f"{dst}/{tag}_ncu_launches_summary.txt",
+               "# ncu launch list of ONE step (config 2: 64 x 30 s, eager launches, 180 kernels) -- gpu__time_duration.sum, --clock-control none\n"
                "# cold-cache, serialised: compare SHARES with bench.py's event-timed `kernels`, not absolutes")
 print(open(f"{dst}/{tag}_ncu_launches_summary.txt").read())
 
 # DRAM bytes (read + write) per launch for bench.py's roofline.traffic, from the 17-launch full capture (launch order is fixed)
-ORDER = ["mel_logmel", "mel_normalize", "conv1", "conv2_igemm", "conv3_igemm", "conv_out_gemm", "conv1", "conv2_igemm", "conv3_igemm",
-         "conv_out_gemm", "layernorm", "gemm_qkv", "window_attention", "gemm_out_proj", "layernorm", "gemm_fc1", "gemm_fc2"]
+# (fused waveform -> embeddings path: ONE mel launch, conv1 applies the clamp / rescale; 180 launches per step)
+ORDER = ["mel_logmel", "conv1", "conv2_igemm", "conv3_igemm", "conv_out_gemm", "conv1", "conv2_igemm", "conv3_igemm",
+         "conv_out_gemm", "layernorm", "gemm_qkv", "window_attention", "gemm_out_proj", "layernorm", "gemm_fc1", "gemm_fc2", "layernorm"]
+_names = [r[[i for i, n in enumerate(list(csv.reader(open(f"{src}/{tag}_step_full2_raw.csv")))[0]) if n == "Kernel Name"][0]]
+          for r in list(csv.reader(open(f"{src}/{tag}_step_full2_raw.csv")))[2:]]
+_key = {"mel_logmel": "mel_logmel", "conv1": "conv1_gelu", "layernorm": "layernorm", "window_attention": "window_attention"}
+for _o, _n in zip(ORDER, _names):  # the fixed order must match what was captured
+    assert (_key[_o] in _n) if _o in _key else ("gemm_bf16_sm100" in _n), (_o, _n)
 rows = list(csv.reader(open(f"{src}/{tag}_step_full2_raw.csv")))
 h, units = rows[0], rows[1]
 idx = {n: i for i, n in enumerate(h)}
