@@ -469,6 +469,11 @@ def main():
     from qwen3_asr_mlx_b200 import AudioEncoder, AudioEncoderConfig, weights
 
     torch.cuda.set_device(local_rank)
+    host_cores = None
+    if world > 1 and os.environ.get("QASR_BIND_HOST", "1") != "0":
+        from qwen3_asr_mlx_b200 import launcher as _launcher
+
+        host_cores = _launcher.bind_host_to_gpu(local_rank)  # before any pinned allocation (first-touch NUMA placement)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = load_peaks()
@@ -646,6 +651,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": "configs[1]: batch 64 x 30 s utterances per GPU, mel+encoder bf16 (fp32 accumulate, fp32 mel), Qwen3-ASR-1.7B arch random-init seed 1234",
+                       "host_binding": (f"rank 0 bound to the {len(host_cores)} cores NVML reports local to its GPU" if host_cores else "none"),
                        "utterances_per_gpu": UTTS_PER_GPU, "utterance_seconds": UTT_SECONDS, "tokens_per_gpu": n_tok, "parallelism": f"dp{world} (one process per GPU, no forward collective)",
                        "l2": "no flush: per-step working set (~5 GB of activations, 123 MB audio in, 204 MB embeddings out) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(audio_np[0].nbytes), "d2h_bytes_per_step": int(out_np[0].nbytes),

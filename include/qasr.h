@@ -117,6 +117,16 @@ int qasr_encode(qasr_handle* h, const float* mel_dev, const int64_t* frame_offse
 int qasr_encode_audio(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch,
                       void* emb_dev, int out_dtype, int64_t* token_offsets_out, void* stream);
 
+/* The same call split in two for callers that ship the embeddings elsewhere while they are being produced (the
+ * data-parallel launcher pushes each finished row block to its NVLink peers): qasr_encode_audio_hidden runs the mel, the
+ * conv stem and the transformer layers (encoder.py:235-317) and leaves the final hidden states in the handle;
+ * qasr_project_rows then applies ln_post -> proj1 -> GELU -> proj2 (encoder.py:319-321) to rows [row0, row0 + n_rows) of
+ * that call, in any blocking and order, writing row `row0` at emb_dev.  Results are bit-identical to qasr_encode_audio.
+ * The hidden states are valid until the next mel / encode call on the handle (QASR_ERR_STATE otherwise). */
+int qasr_encode_audio_hidden(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch,
+                             int64_t* token_offsets_out, void* stream);
+int qasr_project_rows(qasr_handle* h, int64_t row0, int64_t n_rows, void* emb_dev, int out_dtype, void* stream);
+
 /* ---- host-pointer entry points (H2D / D2H inside the call, synchronous on return) ---- */
 int qasr_mel_host(qasr_handle* h, const float* audio_host, const int64_t* sample_offsets, int32_t batch,
                   float* mel_host);

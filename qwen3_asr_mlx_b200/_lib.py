@@ -79,6 +79,8 @@ _SIGNATURES = {
     "qasr_encode_audio": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "qasr_mel_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p]),
     "qasr_encode_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int, POINTER(c_int64)]),
+    "qasr_encode_audio_hidden": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, POINTER(c_int64), c_void_p]),
+    "qasr_project_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "qasr_encode_audio_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int, POINTER(c_int64)]),
     "qasr_encode_audio_host_async": (c_int, [c_void_p, c_int32, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int, POINTER(c_int64)]),
     "qasr_host_wait": (c_int, [c_void_p, c_int32]),

@@ -147,12 +147,17 @@ struct qasr_handle {
   cudaEvent_t pin_event = nullptr;
   bool pin_event_pending = false;
   // CUDA-graph replay of whole calls (keyed by entry point, pointers, dtype and offsets)
+  // hidden-state calls: the lane whose residual stream holds the last qasr_encode_audio_hidden result, and its row count
+  Lane* hidden_lane = nullptr;
+  long long hidden_tokens = 0;
   bool use_graphs = true;
+  size_t graph_cap = 64;  // cached whole-call graphs (QASR_GRAPH_CACHE); a ragged job cycles through one graph per sub-batch
   bool capturing = false;
   struct GraphEntry {
     uint64_t key = 0;
     cudaGraphExec_t exec = nullptr;
     uint8_t* pin = nullptr;  // this graph's own table staging (memcpy nodes read it at every replay)
+    long long hidden_tokens = -1;  // >= 0: a hidden-state call (rows left in lane 0's residual stream)
     std::vector<long long> token_offsets;
     uint64_t launches = 0;   // kernels per replay (for stats)
     uint64_t last_use = 0;
@@ -563,6 +568,32 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
 // mel + ... -> embeddings for the utterances [0, B) described by ABSOLUTE frame offsets (frame_offsets[0] may be > 0:
 // a lane's share starts in the middle of the packed mel buffer), on one lane's workspace and one stream.
 // toffs (B + 1 entries, relative to the share's first token) is filled in.
+// Projector (ln_post -> proj1 + GELU -> proj2, encoder.py:319-321) over rows [r0, r0 + nr) of a lane's residual stream;
+// `out` is where row r0 goes.  Every row's result is independent of the block it is computed in (per-row LayerNorm, fixed
+// K order in the GEMMs), so any blocking gives bit-identical embeddings.
+int project_rows(qasr_handle* h, Lane& ln, long long r0, int nr, void* out, int out_dtype, cudaStream_t st) {
+  const qasr_config& c = h->cfg;
+  const int D = c.d_model;
+  int rc;
+  std::string e;
+  const float* x = static_cast<const float*>(ln.x.p) + r0 * D;
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(ln.xn.p) + r0 * D;
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(ln.hbuf.p) + r0 * D;
+  CUtensorMap tm_xn = ln.tm_xn, tm_p1 = ln.tm_p1;
+  if (r0 != 0) {  // A operands of a row block: maps that start at the block and are clipped to it (rows past it read as zero)
+    if (!make_tmap_rows(&tm_xn, xn, nr, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+    if (!make_tmap_rows(&tm_p1, hb, nr, D, D, kBlockM, &e)) return fail(h, QASR_ERR_CUDA, e);
+  }
+  if ((rc = layernorm(h, x, h->lnp_g, h->lnp_b, xn, nr, st))) return rc;
+  if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_PROJ, tm_xn, h->tm_proj1_w, nr, D, D, hb, D, h->proj1_b, st))) return rc;
+  if (out_dtype == QASR_F32) {
+    if ((rc = dense<EPI_STORE_F32>(h, QASR_PROF_GEMM_PROJ, tm_p1, h->tm_proj2_w, nr, c.output_dim, D, out, c.output_dim, h->proj2_b, st))) return rc;
+  } else {
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_PROJ, tm_p1, h->tm_proj2_w, nr, c.output_dim, D, out, c.output_dim, h->proj2_b, st))) return rc;
+  }
+  return QASR_OK;
+}
+
 int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
                 int out_dtype, long long* toffs, cudaStream_t st, const unsigned* utt_max = nullptr, int utt_base = 0) {
   const qasr_config& c = h->cfg;
@@ -704,15 +735,15 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
   }
   if (h->debug) QCUDA(h, cudaMemcpyAsync(h->dbg_hidden.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
 
-  // ---- projector (encoder.py:319-321)
-  if ((rc = layernorm(h, x, h->lnp_g, h->lnp_b, xn, ni, st))) return rc;
-  if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_PROJ, ln.tm_xn, h->tm_proj1_w, ni, D, D, hb, D, h->proj1_b, st))) return rc;
-  if (out_dtype == QASR_F32) {
-    if ((rc = dense<EPI_STORE_F32>(h, QASR_PROF_GEMM_PROJ, ln.tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
-  } else {
-    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_PROJ, ln.tm_p1, h->tm_proj2_w, ni, c.output_dim, D, emb_dev, c.output_dim, h->proj2_b, st))) return rc;
+  // ---- projector (encoder.py:319-321); a hidden-state call (qasr_encode_audio_hidden) stops here and leaves it to
+  // qasr_project_rows, which runs it over row blocks of the caller's choice
+  h->hidden_lane = nullptr;
+  if (!emb_dev) {
+    h->hidden_lane = &ln;
+    h->hidden_tokens = n;
+    return QASR_OK;
   }
-  return QASR_OK;
+  return project_rows(h, ln, 0, ni, emb_dev, out_dtype, st);
 }
 
 long long chunks_of(long long frames) { return (frames + kChunkFrames - 1) / kChunkFrames; }
@@ -723,7 +754,7 @@ long long chunks_of(long long frames) { return (frames + kChunkFrames - 1) / kCh
 int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_offsets, int B, void* emb_dev,
                 int out_dtype, int64_t* token_offsets_out, cudaStream_t st, const unsigned* utt_max = nullptr) {
   if (!h->finalized) return fail(h, QASR_ERR_STATE, "weights not finalised (call qasr_finalize_weights)");
-  if (!mel_dev || !frame_offsets || !emb_dev || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");
+  if (!mel_dev || !frame_offsets || B <= 0) return fail(h, QASR_ERR_INVALID, "qasr_encode: bad argument");  // emb_dev == nullptr: hidden-state call
   if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
   if (frame_offsets[0] != 0) return fail(h, QASR_ERR_INVALID, "frame_offsets[0] must be 0");
   long long total_chunks = 0;
@@ -732,7 +763,7 @@ int encode_impl(qasr_handle* h, const float* mel_dev, const long long* frame_off
     total_chunks += chunks_of(frame_offsets[u + 1] - frame_offsets[u]);
   }
   int split = B;  // utterances [0, split) -> lane 0, [split, B) -> lane 1
-  if (h->two_lanes && !h->debug && B >= 2 && total_chunks >= h->lane_min_chunks) {
+  if (h->two_lanes && !h->debug && emb_dev && B >= 2 && total_chunks >= h->lane_min_chunks) {
     long long acc = 0, best = -1;
     for (int u = 0; u + 1 < B; ++u) {
       acc += chunks_of(frame_offsets[u + 1] - frame_offsets[u]);
@@ -815,6 +846,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
     if (v > 0) h->stem_group = v;
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
+  if (const char* gc = getenv("QASR_GRAPH_CACHE")) h->graph_cap = static_cast<size_t>(atoi(gc) > 1 ? atoi(gc) : 1);
   if (const char* mo = getenv("QASR_MEL_ONE_PASS")) h->mel_one_pass = atoi(mo) != 0;
   if (const char* ls = getenv("QASR_LANES")) h->two_lanes = atoi(ls) >= 2;
   if (const char* lm = getenv("QASR_LANE_MIN_CHUNKS")) h->lane_min_chunks = atoll(lm);
@@ -1053,7 +1085,7 @@ int qasr_reserve(qasr_handle* h, int64_t total_frames, int32_t batch) {
 // own pinned table staging included) and from then on the whole call is one cudaGraphLaunch.
 namespace {
 
-enum CallKind : int { CALL_MEL = 1, CALL_ENCODE = 2, CALL_ENCODE_AUDIO = 3 };
+enum CallKind : int { CALL_MEL = 1, CALL_ENCODE = 2, CALL_ENCODE_AUDIO = 3, CALL_ENCODE_AUDIO_HIDDEN = 4 };
 struct CallArgs {
   int kind;
   const float* in;
@@ -1105,7 +1137,7 @@ int call_prepare(qasr_handle* h, const CallArgs& c, size_t* pin_bytes) {
   const long long chunks = frames / kChunkFrames + c.B;
   const long long windows = chunks * kTokensPerChunk / window_tokens(h->cfg) + c.B;
   *pin_bytes = 2 * pin_bytes_for(c.B, chunks, windows);
-  if (c.kind == CALL_ENCODE_AUDIO && frames > h->cap_mel_frames) {
+  if ((c.kind == CALL_ENCODE_AUDIO || c.kind == CALL_ENCODE_AUDIO_HIDDEN) && frames > h->cap_mel_frames) {
     int rc;
     if ((rc = dev_alloc(h, h->mel_scratch, static_cast<size_t>(frames) * kMelBins * 4, false))) return rc;
     h->cap_mel_frames = frames;
@@ -1116,7 +1148,8 @@ int call_prepare(qasr_handle* h, const CallArgs& c, size_t* pin_bytes) {
 int dispatch(qasr_handle* h, const CallArgs& c, cudaStream_t user_stream) {
   int rc;
   if ((rc = check_device(h))) return rc;
-  if (!c.in || !c.out || !c.offs || c.B <= 0) return fail(h, QASR_ERR_INVALID, "bad argument (null pointer or empty batch)");
+  if (!c.in || (!c.out && c.kind != CALL_ENCODE_AUDIO_HIDDEN) || !c.offs || c.B <= 0)
+    return fail(h, QASR_ERR_INVALID, "bad argument (null pointer or empty batch)");
   // The legacy NULL stream cannot be captured: run on a private stream, ordered after / before it by events.
   cudaStream_t st = user_stream;
   const bool redirect = (user_stream == nullptr || user_stream == cudaStreamLegacy);
@@ -1134,6 +1167,8 @@ int dispatch(qasr_handle* h, const CallArgs& c, cudaStream_t user_stream) {
       QCUDA(h, cudaGraphLaunch(g.exec, st));
       if (c.toffs_out)
         for (size_t i = 0; i < g.token_offsets.size(); ++i) c.toffs_out[i] = g.token_offsets[i];
+      h->hidden_lane = g.hidden_tokens >= 0 ? &h->lanes[0] : nullptr;
+      h->hidden_tokens = g.hidden_tokens >= 0 ? g.hidden_tokens : 0;
       h->stats.kernel_launches += g.launches;
       g.last_use = ++h->use_clock;
       done = true;
@@ -1169,11 +1204,15 @@ int dispatch(qasr_handle* h, const CallArgs& c, cudaStream_t user_stream) {
       if (graph) cudaGraphDestroy(graph);
       if (e3 == cudaSuccess) {
         if (c.toffs_out && c.kind != CALL_MEL) ge.token_offsets.assign(c.toffs_out, c.toffs_out + c.B + 1);
+        ge.hidden_tokens = (c.kind == CALL_ENCODE_AUDIO_HIDDEN && h->hidden_lane) ? h->hidden_tokens : -1;
         ge.last_use = ++h->use_clock;
-        if (h->graphs.size() >= 8) {  // evict the least recently used graph
+        if (h->graphs.size() >= h->graph_cap) {  // evict the least recently used graph
           size_t victim = 0;
           for (size_t i = 1; i < h->graphs.size(); ++i)
             if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+          // A working set larger than the cache would otherwise re-capture (and cudaFreeHost = device sync) on every call of
+          // a cyclic job: an evicted shape stays eager from now on.
+          h->seen[h->graphs[victim].key].first = -(1 << 30);
           cudaGraphExecDestroy(h->graphs[victim].exec);
           cudaFreeHost(h->graphs[victim].pin);
           h->graphs.erase(h->graphs.begin() + victim);
@@ -1229,7 +1268,39 @@ int qasr_encode_audio(qasr_handle* h, const float* audio_dev, const int64_t* sam
 }
 
 // Host-pointer flavours: H2D, the device entry point, D2H, all on the handle's private stream.
+int qasr_encode_audio_hidden(qasr_handle* h, const float* audio_dev, const int64_t* sample_offsets, int32_t batch,
+                             int64_t* token_offsets_out, void* stream) {
+  if (!h) return fail(nullptr, QASR_ERR_INVALID, "null handle");
+  CallArgs c{CALL_ENCODE_AUDIO_HIDDEN, audio_dev, nullptr, sample_offsets, batch, QASR_BF16, token_offsets_out};
+  return dispatch(h, c, static_cast<cudaStream_t>(stream));
+}
+
+int qasr_project_rows(qasr_handle* h, int64_t row0, int64_t n_rows, void* emb_dev, int out_dtype, void* stream) {
+  if (!h || !emb_dev) return fail(h, QASR_ERR_INVALID, "qasr_project_rows: bad argument");
+  if (out_dtype != QASR_F32 && out_dtype != QASR_BF16) return fail(h, QASR_ERR_INVALID, "bad out_dtype");
+  int rc;
+  if ((rc = check_device(h))) return rc;
+  if (!h->hidden_lane) return fail(h, QASR_ERR_STATE, "qasr_project_rows: no hidden states (call qasr_encode_audio_hidden first)");
+  if (row0 < 0 || n_rows <= 0 || row0 + n_rows > h->hidden_tokens)
+    return fail(h, QASR_ERR_INVALID, "qasr_project_rows: rows outside the last hidden-state call");
+  if (reinterpret_cast<uintptr_t>(emb_dev) & 15) return fail(h, QASR_ERR_INVALID, "emb_dev must be 16-byte aligned");
+  cudaStream_t user_stream = static_cast<cudaStream_t>(stream), st = user_stream;
+  const bool redirect = (user_stream == nullptr || user_stream == cudaStreamLegacy);
+  if (redirect) {  // same stream the hidden-state call ran on
+    QCUDA(h, cudaEventRecord(h->ev_in, user_stream));
+    QCUDA(h, cudaStreamWaitEvent(h->own_stream, h->ev_in, 0));
+    st = h->own_stream;
+  }
+  if ((rc = project_rows(h, *h->hidden_lane, row0, static_cast<int>(n_rows), emb_dev, out_dtype, st))) return rc;
+  if (redirect) {
+    QCUDA(h, cudaEventRecord(h->ev_out, h->own_stream));
+    QCUDA(h, cudaStreamWaitEvent(user_stream, h->ev_out, 0));
+  }
+  return QASR_OK;
+}
+
 namespace {
+
 int host_call(qasr_handle* h, int kind, const float* in_host, size_t in_bytes, const int64_t* offs, int32_t batch,
               void* out_host, size_t out_bytes, int out_dtype, int64_t* toffs_out) {
   int rc;

@@ -199,6 +199,30 @@ class AudioEncoder:
                                         ctypes.c_void_p(out.data_ptr()), cdt, runtime.i64_ptr(toffs), h.stream_ptr()))
         return DeviceArray(out), toffs
 
+    def encode_packed_audio_hidden(self, packed_audio: torch.Tensor, soffs: np.ndarray) -> Tuple[int, np.ndarray]:
+        """``qasr_encode_audio_hidden``: mel + conv stem + transformer layers of a packed batch (encoder.py:235-317); the
+        final hidden states stay in the handle for :meth:`project_rows`.  Returns ``(n_tokens, token_offsets)``."""
+        self._ensure_weights()
+        h = self._handle
+        B = len(soffs) - 1
+        toffs = np.zeros(B + 1, dtype=np.int64)
+        h.check(h.lib.qasr_encode_audio_hidden(h.ptr, ctypes.c_void_p(packed_audio.data_ptr()), runtime.i64_ptr(soffs), B,
+                                               runtime.i64_ptr(toffs), h.stream_ptr()))
+        return int(toffs[-1]), toffs
+
+    def project_rows(self, row0: int, out: torch.Tensor) -> torch.Tensor:
+        """``qasr_project_rows``: ln_post -> proj1 -> GELU -> proj2 (encoder.py:319-321) for rows
+        ``[row0, row0 + len(out))`` of the last :meth:`encode_packed_audio_hidden` call, written into ``out``
+        (contiguous ``(rows, output_dim)`` float32 / bfloat16 CUDA tensor).  Any blocking of the rows gives the same bits
+        as one :meth:`encode_packed_audio` call."""
+        h = self._handle
+        if out.ndim != 2 or out.shape[1] != self.config.output_dim or not out.is_contiguous() or out.data_ptr() % 16 or \
+                out.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out must be a contiguous, 16-byte aligned (rows, output_dim) float32 / bfloat16 tensor")
+        cdt = _lib.QASR_BF16 if out.dtype == torch.bfloat16 else _lib.QASR_F32
+        h.check(h.lib.qasr_project_rows(h.ptr, int(row0), int(out.shape[0]), ctypes.c_void_p(out.data_ptr()), cdt, h.stream_ptr()))
+        return out
+
     def find_split_points(self, audio: torch.Tensor, chunk_samples: int, search_samples: int, frame_samples: int = 480,
                           return_energy: bool = False):
         """Cut positions for long audio on the device (reference ``_find_split_points``, model.py:454-513):

@@ -21,6 +21,40 @@ TOKENS_PER_CHUNK = 13
 HOP = 160
 
 
+def bind_host_to_gpu(device: int) -> Optional[List[int]]:
+    """Pin this process (and the pinned host buffers it allocates afterwards: first-touch NUMA placement) to the CPU cores
+    NVML reports as local to ``device``.  With one process per GPU on a two-socket node, the per-step host<->device copies
+    of the end-to-end path (123 MB in, 204 MB out per step and rank for config 2) otherwise cross the socket interconnect
+    for half of the ranks.  Returns the core list, or None when NVML / the affinity call is unavailable (nothing changed).
+    Honours CUDA_VISIBLE_DEVICES through the device's PCI bus id."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), "pci_bus_id") else None
+        handle = None
+        if bus is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hd = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if int(pynvml.nvmlDeviceGetPciInfo(hd).bus) == int(bus):
+                    handle = hd
+                    break
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        allowed = os.sched_getaffinity(0)
+        cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b in allowed]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:  # no NVML, container without the affinity syscall, ...: leave the placement to the OS
+        return None
+
+
 def conv_output_length(n: int) -> int:
     for _ in range(3):
         n = (n - 1) // 2 + 1
@@ -315,13 +349,16 @@ class PeerBlockGather:
 
 def encode_contiguous_sharded(encoder, packed_audio: torch.Tensor, n_samples: Sequence[int], rank: int, world_size: int,
                               gather: Optional[PeerBlockGather] = None, tokens_per_call: int = 32768,
-                              out_dtype: str = "bfloat16"):
+                              out_dtype: str = "bfloat16", tail_blocks: int = 4, tail_min_rows: int = 2048):
     """BASELINE config 3 on ``world_size`` GPUs with the gather hidden behind the compute.
 
     ``n_samples``: lengths of ALL utterances (original order); ``packed_audio``: THIS rank's share (``contiguous_partition``
     over token counts), packed back to back on the device.  The share is encoded in consecutive sub-batches of at most
     ``tokens_per_call`` tokens -- slices of ``packed_audio``, no host-side packing -- each writing its embeddings at their
     final rows of the symmetric buffer and pushed to the peers while the next sub-batch computes.
+    The LAST sub-batch has nothing to hide its push behind, so its projector runs in ``tail_blocks`` row blocks
+    (``encode_packed_audio_hidden`` + ``project_rows``: same bits) and every block is pushed as soon as it exists: only
+    the last block's transfer (1 / ``tail_blocks`` of a sub-batch; blocks of at least ``tail_min_rows`` rows) stays exposed.
     Returns ``(embeddings, token_offsets (B+1,), my_indices)``; with ``gather=None`` the embeddings are this rank's rows only."""
     costs = [tokens_for_samples(int(n)) for n in n_samples]
     parts = contiguous_partition(costs, world_size)
@@ -344,15 +381,27 @@ def encode_contiguous_sharded(encoder, packed_audio: torch.Tensor, n_samples: Se
     n_sub = max(1, -(-my_rows // max(1, int(tokens_per_call))))
     even = -(-my_rows // n_sub) if my_rows else tokens_per_call
     longest = max((costs[i] for i in mine), default=0)
-    for sub in split_by_budget(mine, costs, min(int(tokens_per_call), even + longest)):
+    subs = split_by_budget(mine, costs, min(int(tokens_per_call), even + longest))
+    for k, sub in enumerate(subs):
         so = np.zeros(len(sub) + 1, dtype=np.int64)
         np.cumsum([int(n_samples[i]) for i in sub], out=so[1:])
         rows = sum(costs[i] for i in sub)
-        _, toffs = encoder.encode_packed_audio(packed_audio[sample_pos: sample_pos + int(so[-1])], so, out_dtype=out_dtype,
-                                               out=local[row_pos: row_pos + rows])
-        assert int(toffs[-1]) == rows, "token count mismatch between host rule and library"
-        if gather is not None:
-            gather.push(row_base + row_pos, rows)
+        audio = packed_audio[sample_pos: sample_pos + int(so[-1])]
+        nblk = min(int(tail_blocks), rows // max(1, int(tail_min_rows))) if (gather is not None and gather.peers and k == len(subs) - 1) else 1
+        if nblk > 1:
+            n_hidden, _ = encoder.encode_packed_audio_hidden(audio, so)
+            assert n_hidden == rows, "token count mismatch between host rule and library"
+            step = -(-rows // nblk)
+            step += (-step) % min(256, max(1, int(tail_min_rows)))  # whole 256-row GEMM tiles per block
+            for r0 in range(0, rows, step):
+                nr = min(step, rows - r0)
+                encoder.project_rows(r0, local[row_pos + r0: row_pos + r0 + nr])
+                gather.push(row_base + row_pos + r0, nr)
+        else:
+            _, toffs = encoder.encode_packed_audio(audio, so, out_dtype=out_dtype, out=local[row_pos: row_pos + rows])
+            assert int(toffs[-1]) == rows, "token count mismatch between host rule and library"
+            if gather is not None:
+                gather.push(row_base + row_pos, rows)
         sample_pos += int(so[-1])
         row_pos += rows
     if gather is not None:

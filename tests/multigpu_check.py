@@ -54,7 +54,8 @@ def main():
     for dt, name in ((torch.float32, "float32"), (torch.bfloat16, "bfloat16")):
         bg = launcher.PeerBlockGather(int(offs[-1]) + 16, cfg.output_dim, dtype=dt)
         for _ in range(2):
-            emb_c, offs3, mine3 = launcher.encode_contiguous_sharded(enc, packed, lengths, rank, world, gather=bg, tokens_per_call=2048, out_dtype=name)
+            emb_c, offs3, mine3 = launcher.encode_contiguous_sharded(enc, packed, lengths, rank, world, gather=bg, tokens_per_call=2048, out_dtype=name,
+                                                                         tail_min_rows=256)  # exercises the tail-block projector path
         want = emb if dt == torch.float32 else None
         if want is None:  # bf16 output: compare with a bf16 single-GPU encode of the whole batch (every rank computes it)
             want = enc.encode_audio_batch(audios, out_dtype="bfloat16")[0].tensor

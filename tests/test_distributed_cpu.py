@@ -56,6 +56,20 @@ class _FakePackedEncoder:
             row += t
         return out, np.concatenate([[0], np.cumsum([launcher.tokens_for_samples(int(b - a)) for a, b in zip(soffs[:-1], soffs[1:])])])
 
+    # tail-block protocol of the launcher: the "hidden states" of the last call stay in the encoder, the projector fills
+    # row blocks of the caller's choice
+    def encode_packed_audio_hidden(self, audio, soffs):
+        toffs = np.concatenate([[0], np.cumsum([launcher.tokens_for_samples(int(b - a)) for a, b in zip(soffs[:-1], soffs[1:])])])
+        self._hidden = torch.empty((int(toffs[-1]), DIM))
+        self.encode_packed_audio(audio, soffs, out=self._hidden)
+        self.hidden_calls = getattr(self, "hidden_calls", 0) + 1
+        return int(toffs[-1]), toffs
+
+    def project_rows(self, row0, out):
+        out.copy_(self._hidden[row0: row0 + out.shape[0]])
+        self.projected_blocks = getattr(self, "projected_blocks", 0) + 1
+        return out
+
 
 class _GlooBlockGather:
     """Stand-in for launcher.PeerBlockGather on CPU: same begin / rows / push / finish protocol, the pushes are delivered
@@ -65,6 +79,7 @@ class _GlooBlockGather:
         self.buf = torch.full((rows, DIM), -1.0)
         self.dtype = torch.float32
         self.blocks = []
+        self.peers = [r for r in range(dist.get_world_size()) if r != dist.get_rank()]
 
     def begin(self):
         dist.barrier()
@@ -110,10 +125,13 @@ def _worker(rank, world, port, q):
         share = launcher.contiguous_partition(costs, world)[rank]
         packed = torch.cat([torch.full((N_SAMPLES[i],), float(i)) for i in share])
         g = _GlooBlockGather(sum(costs))
+        fake = _FakePackedEncoder()
         for _ in range(2):  # the buffer is reused by a second gather
-            emb2, offs2, mine2 = launcher.encode_contiguous_sharded(_FakePackedEncoder(), packed, N_SAMPLES, rank, world, gather=g,
-                                                                    tokens_per_call=150, out_dtype="float32")
+            emb2, offs2, mine2 = launcher.encode_contiguous_sharded(fake, packed, N_SAMPLES, rank, world, gather=g,
+                                                                    tokens_per_call=150, out_dtype="float32", tail_min_rows=32)
             ok = ok and mine2 == share and bool(torch.equal(emb2, _expected())) and int(offs2[-1]) == emb2.shape[0]
+        # the last sub-batch of every pass went through the hidden-state call and was projected + pushed block by block
+        ok = ok and getattr(fake, "hidden_calls", 0) == 2 and getattr(fake, "projected_blocks", 0) >= 4
         loc, _, _ = launcher.encode_contiguous_sharded(_FakePackedEncoder(), packed, N_SAMPLES, rank, world, gather=None, out_dtype="float32")
         ok = ok and bool(torch.equal(loc, _expected()[int(offs2[share[0]]): int(offs2[share[-1] + 1])]))
         q.put((rank, ok, mine))

@@ -567,3 +567,60 @@ def test_outputs_stay_inside_their_buffers(small):
         torch.cuda.synchronize()
         assert bool((bigm[:pad] == 777.0).all()) and bool((bigm[pad + 128 * frames:] == 777.0).all())
         assert bool(torch.equal(melv, ref_mel.tensor))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_hidden_plus_row_block_projector_equals_one_call(small, dtype):
+    """qasr_encode_audio_hidden + qasr_project_rows (the launcher's tail-block path): any blocking of the projector rows,
+    in any order, gives the bits of one qasr_encode_audio call -- eager, captured and replayed."""
+    import torch
+
+    from qwen3_asr_mlx_b200 import _lib
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(91)
+    lens = [16000 * 11 + 123, 16000 * 3, 4000, 16000 * 29 + 1]
+    x = np.concatenate([synth(rng, n) for n in lens])
+    soffs = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=soffs[1:])
+    audio = torch.from_numpy(x).cuda()
+    tdt = torch.bfloat16 if dtype == "bfloat16" else torch.float32
+    ref, toffs = enc.encode_packed_audio(audio, soffs, out_dtype=dtype)
+    ref = ref.tensor.clone()
+    n = int(toffs[-1])
+    for blocks in ([n], [256, n - 256], [100, 7, n - 107], [n - 1, 1]):
+        for _ in range(3):  # eager, capture, replay of the hidden-state call
+            n_hidden, toffs2 = enc.encode_packed_audio_hidden(audio, soffs)
+            assert n_hidden == n and np.array_equal(toffs2, toffs)
+            out = torch.full((n, cfg.output_dim), float("nan"), dtype=tdt, device="cuda")
+            starts = np.concatenate([[0], np.cumsum(blocks)[:-1]])
+            for r0, nr in reversed(list(zip(starts, blocks))):  # order does not matter
+                enc.project_rows(int(r0), out[int(r0): int(r0) + int(nr)])
+            assert torch.equal(out.view(torch.int16 if tdt == torch.bfloat16 else torch.int32),
+                               ref.view(torch.int16 if tdt == torch.bfloat16 else torch.int32))
+    with pytest.raises(ValueError):
+        enc.project_rows(n - 3, torch.empty((8, cfg.output_dim), dtype=tdt, device="cuda"))  # rows past the call
+    enc.encode_packed_audio(audio, soffs, out_dtype=dtype)  # an ordinary call drops the hidden state
+    with pytest.raises(_lib.QasrError):
+        enc.project_rows(0, torch.empty((8, cfg.output_dim), dtype=tdt, device="cuda"))
+
+
+def test_many_call_shapes_keep_their_graphs(small):
+    """A ragged job cycles through one call shape per sub-batch (config 3: 26 of them): every shape keeps its captured
+    graph (cache of 64) instead of being re-captured on every pass, and results stay those of the eager pass."""
+    import torch
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(92)
+    shapes = [16000 + 160 * k for k in range(20)]
+    audio = [torch.from_numpy(synth(rng, n)).cuda() for n in shapes]
+    outs = [torch.empty((enc.num_tokens(n // 160), cfg.output_dim), dtype=torch.float32, device="cuda") for n in shapes]
+    first = None
+    for p in range(4):
+        for a, o, n in zip(audio, outs, shapes):
+            enc.encode_packed_audio(a, np.array([0, n], dtype=np.int64), out=o)
+        got = [o.cpu().numpy().copy() for o in outs]
+        if first is None:
+            first = got
+        assert all(np.array_equal(g, f) for g, f in zip(got, first))
+    torch.cuda.synchronize()
