@@ -370,7 +370,8 @@ def measure_sharded_configs(enc, cfg, rank, world, reps=3):
     del audio, gather
     torch.cuda.empty_cache()
 
-    x = torch.from_numpy(long_file()).cuda()
+    x_host = long_file()
+    x = torch.from_numpy(x_host).cuda()
     so = np.array([0, x.numel()], dtype=np.int64)
     if world == 1:
         o = torch.empty((15600, cfg.output_dim), dtype=torch.bfloat16, device="cuda")
@@ -378,6 +379,43 @@ def measure_sharded_configs(enc, cfg, rank, world, reps=3):
             enc.encode_packed_audio(x, so, out_dtype="bfloat16", out=o)
         ms4, _ = _timed_max(lambda: enc.encode_packed_audio(x, so, out_dtype="bfloat16", out=o), 1, 5)
         out["config4_20min_single_pass"] = {"ms": ms4, "audio_s_per_s": 1200.0 / (ms4 / 1e3), "tokens": 15600, "windows": 150}
+        # config 4 (ii), SURVEY 8d: chunk_duration = 30 s, so the long-audio splitter really cuts (model.py:400-441): one upload,
+        # frame RMS + windowed argmin on the device, every segment encoded with its own mel maximum as ONE varlen batch
+        cuts = enc.find_split_points(x, 30 * SR, 5 * SR)
+        bounds = [0]
+        for c in [int(c) for c in cuts] + [int(x.numel())]:  # empty slices are skipped, like model.py:408-413
+            if c > bounds[-1]:
+                bounds.append(c)
+        so_seg = np.asarray(bounds, dtype=np.int64)
+
+        def chunked():
+            enc.find_split_points(x, 30 * SR, 5 * SR)
+            return enc.encode_packed_audio(x, so_seg, out_dtype="bfloat16")
+
+        for _ in range(3):
+            chunked()
+        ms4c, (embc, toffc) = _timed_max(chunked, 1, 5)
+        out["config4_20min_chunked_30s"] = {"ms": ms4c, "audio_s_per_s": 1200.0 / (ms4c / 1e3), "segments": len(bounds) - 1, "tokens": int(toffc[-1]),
+                                            "what": "device splitter (find_split_points: the host reads the cut list back) + one varlen encode of all segments, per-segment mel max"}
+        # config 1: ONE 10 s utterance (latency case; the reference's own CPU-runnable configuration)
+        x1_host = synth(np.random.default_rng(0), 10 * SR)
+        x1 = torch.from_numpy(x1_host).cuda()
+        so1 = np.array([0, 10 * SR], dtype=np.int64)
+        o1 = torch.empty((130, cfg.output_dim), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            enc.encode_packed_audio(x1, so1, out=o1)
+        ms1, _ = _timed_max(lambda: enc.encode_packed_audio(x1, so1, out=o1), 1, 50)
+        pin_in, pin_out = torch.from_numpy(x1_host).pin_memory().numpy(), torch.empty((130, cfg.output_dim), dtype=torch.float32).pin_memory().numpy()
+        for _ in range(3):
+            enc.encode_audio_host(pin_in, so1, pin_out)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            enc.encode_audio_host(pin_in, so1, pin_out)
+        ms1_host = (time.perf_counter() - t0) * 1e3 / 50
+        out["config1_single_10s"] = {"ms_per_call": ms1, "audio_s_per_s": 10.0 / (ms1 / 1e3), "tokens": 130,
+                                     "host_call_ms": ms1_host, "host_call_audio_s_per_s": 10.0 / (ms1_host / 1e3),
+                                     "what": "device-resident call (CUDA-graph replay, 128 x 64 tiles below 1024 rows) and the synchronous host call "
+                                             "qasr_encode_audio_host (pinned buffers, H2D + D2H inside, wall clock)"}
     else:
         g4 = launcher.PeerBlockGather(15600, cfg.output_dim, dtype=torch.bfloat16)
 
