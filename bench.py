@@ -600,6 +600,28 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(e2e_wall_ms) / args.steps
     e2e_value = audio_s_per_step / (e2e_ms / 1e3)
+    # the same pipeline with bf16 embeddings on the wire (half the D2H bytes).  The reference's consumer casts the audio
+    # embeddings to the decoder's embedding dtype -- bf16 for the published checkpoint -- before it uses them
+    # (generate.py:53,71-73), so this is the layout the next stage reads; the headline `e2e` stays on fp32 outputs.
+    out16 = [torch.empty((n_tok, cfg.output_dim), dtype=torch.int16).pin_memory().numpy().view(np.uint16) for _ in range(2)]
+    for s in (0, 1):
+        enc.host_wait(s)
+        enc.encode_audio_host_async(s, audio_np[s], soffs, out16[s])
+    enc.host_wait(0)
+    enc.host_wait(1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        s = i & 1
+        enc.host_wait(s)
+        if i >= 2:
+            checksum += float(out16[s][0, 0])
+        enc.encode_audio_host_async(s, audio_np[s], soffs, out16[s])
+    enc.host_wait(0)
+    enc.host_wait(1)
+    e2e16_wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e16_ms = max_over_ranks(e2e16_wall_ms) / args.steps
     # serial variant for reference: one synchronous qasr_encode_audio_host call per step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     enc.encode_audio_host(audio_np[0], soffs, out_np[0])
@@ -696,7 +718,9 @@ def main():
                     "api": "qasr_encode_audio_host_async + qasr_host_wait, 2 slots (pinned host audio in, pinned host fp32 embeddings out; copies overlap the other slot's kernels)",
                     "timing": "host wall clock around K submitted+completed steps (the pipeline spans 3 streams), max over ranks",
                     "serial_ms_per_step": e2e_serial_ms, "serial_value": audio_s_per_step / (e2e_serial_ms / 1e3),
-                    "serial_api": "qasr_encode_audio_host (one synchronous call per step)"},
+                    "serial_api": "qasr_encode_audio_host (one synchronous call per step)",
+                    "bf16_out_ms_per_step": e2e16_ms, "bf16_out_value": audio_s_per_step / (e2e16_ms / 1e3), "bf16_out_d2h_bytes_per_step": int(out16[0].nbytes),
+                    "bf16_out_note": "same pipeline, bf16 embeddings to the host (what the reference's consumer casts to, generate.py:71-73); not the headline"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
