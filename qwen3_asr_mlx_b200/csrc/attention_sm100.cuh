@@ -39,7 +39,8 @@ constexpr int kAtPCol = 128, kAtOCol = 192;
 
 __global__ void __launch_bounds__(kAtThreads, 1)
 window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const WindowDesc* __restrict__ windows,
-                       int num_windows, int num_heads, int D, __nv_bfloat16* __restrict__ out, float scale_log2e) {
+                       int num_windows, int num_heads, int D, __nv_bfloat16* __restrict__ out, float scale_log2e,
+                       int reverse = 0 /* 1: last window first (serpentine row order between consecutive kernels) */) {
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;                                   // kAtStages x (Q | K | V)
@@ -86,8 +87,9 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++j) {
         const int st = j % kAtStages;
         const uint32_t ph = (j / kAtStages) & 1;
-        const WindowDesc wd = windows[item / num_heads];
-        const int head = item % num_heads;
+        const int it = reverse ? num_items - 1 - item : item;
+        const WindowDesc wd = windows[it / num_heads];
+        const int head = it % num_heads;
         ptx::mbar_wait(&sempty[st], ph ^ 1);
         ptx::mbar_expect_tx(&full[st], kAtStageBytes);
         uint8_t* sb = stage_base + st * kAtStageBytes;
@@ -127,7 +129,7 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
           if (ptx::mbar_test_wait(&p_ready[slot], (j >> 1) & 1)) {
             ptx::tc_fence_after();
             const int item = blockIdx.x + j * gridDim.x;
-            const int len = windows[item / num_heads].len;
+            const int len = windows[(reverse ? num_items - 1 - item : item) / num_heads].len;
             const int ksteps = (len + 15) >> 4;
             const uint8_t* sb = stage_base + st * kAtStageBytes;
             // V tile: 64 dims (one 128-byte swizzle row) per key, 8-key groups 1024 B apart
@@ -152,8 +154,9 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
       const int item = blockIdx.x + j * gridDim.x;
       const int st = group;                      // TMEM slot
       const uint32_t ph = (j >> 1) & 1;
-      const WindowDesc wd = windows[item / num_heads];
-      const int head = item % num_heads;
+      const int it = reverse ? num_items - 1 - item : item;
+      const WindowDesc wd = windows[it / num_heads];
+      const int head = it % num_heads;
       const int len = wd.len;
       const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t tmem_s = tmem_base + lane_addr + st * kAtSlotCols;

@@ -112,11 +112,12 @@ conv1_gelu_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict__ c
 template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      __nv_bfloat16* __restrict__ y, int rows, float eps) {
+                      __nv_bfloat16* __restrict__ y, int rows, float eps, int reverse = 0) {
   constexpr int D = 128 * VPL;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row_fwd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (row_fwd >= rows) return;
+  const int row = reverse ? rows - 1 - row_fwd : row_fwd;  // serpentine: start on the rows the producer wrote last
   const float4* __restrict__ xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
   float4 v[VPL];
   float sum = 0.0f;

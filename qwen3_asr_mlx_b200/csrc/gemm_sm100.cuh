@@ -74,6 +74,9 @@ struct GemmParams {
   const int* row_map;  // [M] destination row or -1
   const float* pe;     // [period, N]
   int pe_period;
+  // 1: tiles are taken from the last M block downwards.  Consecutive kernels of a layer alternate the direction
+  // ("serpentine"), so each starts on the rows its producer wrote last -- the ones still in L2.
+  int reverse_tiles;
 };
 
 // kCta = 2: a pair of CTAs (thread-block cluster of 2, one per SM of a TPC) computes a 256 x BLOCK_N
@@ -169,8 +172,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // a conv box covers rows_per_tile * OW (< 128) pixels: the tail rows of the stage are never written
       const uint32_t a_tx = p.a_tx_bytes > 0 ? static_cast<uint32_t>(p.a_tx_bytes) : static_cast<uint32_t>(L::kABytes);
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-        const int m_blk = (tile / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
-        const int n_blk = tile % p.num_n_tiles;
+        const int tsel = p.reverse_tiles ? num_tiles - 1 - tile : tile;
+        const int m_blk = (tsel / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
+        const int n_blk = tsel % p.num_n_tiles;
         const int b_row0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / kCta);  // this CTA's B rows
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -279,8 +283,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-      const int m_blk = (tile / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
-      const int n_blk = tile % p.num_n_tiles;
+      const int tsel = p.reverse_tiles ? num_tiles - 1 - tile : tile;
+      const int m_blk = (tsel / p.num_n_tiles) * kCta + static_cast<int>(cta_rank);
+      const int n_blk = tsel % p.num_n_tiles;
       const int n0 = n_blk * BLOCK_N;
 
       // Destination row (or pixel) index of this thread's accumulator row, -1 if it is not stored.

@@ -150,6 +150,7 @@ struct qasr_handle {
   // hidden-state calls: the lane whose residual stream holds the last qasr_encode_audio_hidden result, and its row count
   Lane* hidden_lane = nullptr;
   long long hidden_tokens = 0;
+  bool serpentine = true;  // QASR_SERPENTINE=0: every kernel walks the rows upwards
   bool use_graphs = true;
   size_t graph_cap = 64;  // cached whole-call graphs (QASR_GRAPH_CACHE); a ragged job cycles through one graph per sub-batch
   bool capturing = false;
@@ -467,22 +468,22 @@ size_t pin_bytes_for(long long batch, long long chunks, long long windows) {
 }
 
 template <int VPL>
-void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
+void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st, int reverse) {
   // 4 warps per CTA (8 K registers): small enough to co-reside with a persistent GEMM CTA of the other lane
   static const int ln_threads = getenv("QASR_LN_THREADS") ? atoi(getenv("QASR_LN_THREADS")) : 256;
-  layernorm_bf16_kernel<VPL><<<(rows + ln_threads / 32 - 1) / (ln_threads / 32), ln_threads, 0, st>>>(x, g, b, y, rows, 1e-5f);
+  layernorm_bf16_kernel<VPL><<<(rows + ln_threads / 32 - 1) / (ln_threads / 32), ln_threads, 0, st>>>(x, g, b, y, rows, 1e-5f, reverse);
 }
-int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st) {
+int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st, int reverse = 0) {
   ProfScope ps(h, QASR_PROF_LAYERNORM, st, 0.0, 6.0 * rows * h->cfg.d_model);
   switch (h->cfg.d_model / 128) {
-    case 1: launch_ln<1>(x, g, b, y, rows, st); break;
-    case 2: launch_ln<2>(x, g, b, y, rows, st); break;
-    case 3: launch_ln<3>(x, g, b, y, rows, st); break;
-    case 4: launch_ln<4>(x, g, b, y, rows, st); break;
-    case 5: launch_ln<5>(x, g, b, y, rows, st); break;
-    case 6: launch_ln<6>(x, g, b, y, rows, st); break;
-    case 7: launch_ln<7>(x, g, b, y, rows, st); break;
-    case 8: launch_ln<8>(x, g, b, y, rows, st); break;
+    case 1: launch_ln<1>(x, g, b, y, rows, st, reverse); break;
+    case 2: launch_ln<2>(x, g, b, y, rows, st, reverse); break;
+    case 3: launch_ln<3>(x, g, b, y, rows, st, reverse); break;
+    case 4: launch_ln<4>(x, g, b, y, rows, st, reverse); break;
+    case 5: launch_ln<5>(x, g, b, y, rows, st, reverse); break;
+    case 6: launch_ln<6>(x, g, b, y, rows, st, reverse); break;
+    case 7: launch_ln<7>(x, g, b, y, rows, st, reverse); break;
+    case 8: launch_ln<8>(x, g, b, y, rows, st, reverse); break;
     default: return fail(h, QASR_ERR_UNSUPPORTED, "d_model");
   }
   QCUDA(h, cudaGetLastError());
@@ -491,8 +492,9 @@ int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __
 
 template <int EPI>
 int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, int M, int N, int K, void* out,
-          long long ldo, const float* bias, cudaStream_t st) {
+          long long ldo, const float* bias, cudaStream_t st, int reverse = 0) {
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
+  p.reverse_tiles = reverse;
   CUtensorMap tout;
   const CUtensorMap* toutp = nullptr;
   // dense outputs leave through a TMA tile store / reduce (exact row count: rows >= M are clipped by the map)
@@ -709,27 +711,34 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
   const int ni = static_cast<int>(n);
   double attn_flops = 0.0;  // 4 * w^2 * D per window of w tokens (QK^T and PV)
   for (const WindowDesc& w : windows) attn_flops += 4.0 * w.len * w.len * D;
+  // Serpentine row order: every kernel of the chain walks the token rows in the direction opposite to its producer's, so it
+  // starts on the rows that were written last and are still in the 126 MB L2 (activations are 51-204 MB per tensor: with
+  // one direction for all, each kernel starts on rows that were evicted long ago and evicts the rest before it gets there).
+  // Rows are independent in every kernel, so the order changes no result.
+  int dir = 0;  // conv_out wrote x upwards: the first LayerNorm walks down
+  auto next_dir = [&]() { dir = h->serpentine ? !dir : 0; return dir; };
   for (size_t li = 0; li < h->layers.size(); ++li) {
     LayerWeights& L = h->layers[li];
-    if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, ln.tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st))) return rc;
+    if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, ln.tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st, next_dir()))) return rc;
     {
       ProfScope ps(h, QASR_PROF_ATTENTION, st, attn_flops, 8.0 * n * D);
       if (h->attn_tc) {
         const long long items = nwin * H;
         const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
         window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(ln.tm_qkv, static_cast<const WindowDesc*>(ln.d_windows.p),
-                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e);
+                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e, next_dir());
       } else {
+        next_dir();
         window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
             qkv, static_cast<const WindowDesc*>(ln.d_windows.p), attn, D, scale_log2e);
       }
     }
     QCUDA(h, cudaGetLastError());
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, ln.tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st))) return rc;
-    if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st))) return rc;
-    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, ln.tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st))) return rc;
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, ln.tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, ln.tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st, next_dir()))) return rc;
+    if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, ln.tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, ln.tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st, next_dir()))) return rc;
     if (h->debug && li == 0)
       QCUDA(h, cudaMemcpyAsync(h->dbg_layer0.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -846,6 +855,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
     if (v > 0) h->stem_group = v;
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
+  if (const char* sp = getenv("QASR_SERPENTINE")) h->serpentine = atoi(sp) != 0;
   if (const char* gc = getenv("QASR_GRAPH_CACHE")) h->graph_cap = static_cast<size_t>(atoi(gc) > 1 ? atoi(gc) : 1);
   if (const char* mo = getenv("QASR_MEL_ONE_PASS")) h->mel_one_pass = atoi(mo) != 0;
   if (const char* ls = getenv("QASR_LANES")) h->two_lanes = atoi(ls) >= 2;
