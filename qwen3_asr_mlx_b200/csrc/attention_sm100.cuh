@@ -40,7 +40,8 @@ constexpr int kAtPCol = 128, kAtOCol = 192;
 __global__ void __launch_bounds__(kAtThreads, 1)
 window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const WindowDesc* __restrict__ windows,
                        int num_windows, int num_heads, int D, __nv_bfloat16* __restrict__ out, float scale_log2e,
-                       int reverse = 0 /* 1: last window first (serpentine row order between consecutive kernels) */) {
+                       int reverse = 0 /* 1: last window first (serpentine row order between consecutive kernels) */,
+                       unsigned long long qkv_policy = 0 /* L2 eviction priority of the Q/K/V loads (0: none) */) {
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;                                   // kAtStages x (Q | K | V)
@@ -93,9 +94,15 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
         ptx::mbar_wait(&sempty[st], ph ^ 1);
         ptx::mbar_expect_tx(&full[st], kAtStageBytes);
         uint8_t* sb = stage_base + st * kAtStageBytes;
-        ptx::tma_load_2d(sb, &tmap_qkv, &full[st], head * 64, wd.start);
-        ptx::tma_load_2d(sb + kAtTileBytes, &tmap_qkv, &full[st], D + head * 64, wd.start);
-        ptx::tma_load_2d(sb + 2 * kAtTileBytes, &tmap_qkv, &full[st], 2 * D + head * 64, wd.start);
+        if (qkv_policy) {
+          ptx::tma_load_2d_hint(sb, &tmap_qkv, &full[st], head * 64, wd.start, qkv_policy);
+          ptx::tma_load_2d_hint(sb + kAtTileBytes, &tmap_qkv, &full[st], D + head * 64, wd.start, qkv_policy);
+          ptx::tma_load_2d_hint(sb + 2 * kAtTileBytes, &tmap_qkv, &full[st], 2 * D + head * 64, wd.start, qkv_policy);
+        } else {
+          ptx::tma_load_2d(sb, &tmap_qkv, &full[st], head * 64, wd.start);
+          ptx::tma_load_2d(sb + kAtTileBytes, &tmap_qkv, &full[st], D + head * 64, wd.start);
+          ptx::tma_load_2d(sb + 2 * kAtTileBytes, &tmap_qkv, &full[st], 2 * D + head * 64, wd.start);
+        }
       }
     }
   } else if (warp_idx == 1) {

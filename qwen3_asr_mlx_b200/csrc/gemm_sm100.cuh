@@ -77,6 +77,10 @@ struct GemmParams {
   // 1: tiles are taken from the last M block downwards.  Consecutive kernels of a layer alternate the direction
   // ("serpentine"), so each starts on the rows its producer wrote last -- the ones still in L2.
   int reverse_tiles;
+  // L2 eviction priorities (ptx::kL2Evict*; 0 = no hint) of the A-operand loads, the B-operand loads and the fp32 residual
+  // reduction (A_ROWS kernels): activations that are read for the last time leave L2 first, the residual stream -- touched
+  // by four of the seven kernels of a layer -- and the weights stay.
+  unsigned long long a_policy, b_policy, out_policy;
 };
 
 // kCta = 2: a pair of CTAs (thread-block cluster of 2, one per SM of a TPC) computes a 256 x BLOCK_N
@@ -183,8 +187,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if constexpr (kCta == 1) {
             ptx::mbar_expect_tx(&full_bar[stage], a_tx + L::kBBytes);
             if constexpr (kAMode == A_ROWS) {
-              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-              ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, b_row0);
+              if (p.a_policy) ptx::tma_load_2d_hint(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, p.a_policy);
+              else ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+              if (p.b_policy) ptx::tma_load_2d_hint(sb, &tmap_b, &full_bar[stage], kb * kBlockK, b_row0, p.b_policy);
+              else ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, b_row0);
             } else {
               const int tap = kb / p.conv_kc_per_tap;
               const int kc = kb - tap * p.conv_kc_per_tap;
@@ -199,8 +205,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (a_tx + L::kBBytes));
             if constexpr (kAMode == A_ROWS) {
-              ptx::tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * kBlockK, m_blk * kBlockM);
-              ptx::tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * kBlockK, b_row0);
+              if (p.a_policy) ptx::tma_load_2d_cg2_hint(sa, &tmap_a, lead_bar, kb * kBlockK, m_blk * kBlockM, p.a_policy);
+              else ptx::tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * kBlockK, m_blk * kBlockM);
+              if (p.b_policy) ptx::tma_load_2d_cg2_hint(sb, &tmap_b, lead_bar, kb * kBlockK, b_row0, p.b_policy);
+              else ptx::tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * kBlockK, b_row0);
             } else {
               const int tap = kb / p.conv_kc_per_tap;
               const int kc = kb - tap * p.conv_kc_per_tap;
@@ -457,7 +465,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           __syncwarp();
           const int row0 = m_blk * kBlockM + quarter * 32;
           if (lane == 0 && n_ok && row0 < p.M) {
-            if constexpr (kEpi == EPI_RESID_F32) ptx::tma_reduce_add_2d(&tmap_out, stg, n, row0);
+            if constexpr (kEpi == EPI_RESID_F32) {
+              if (p.out_policy) ptx::tma_reduce_add_2d_hint(&tmap_out, stg, n, row0, p.out_policy);
+              else ptx::tma_reduce_add_2d(&tmap_out, stg, n, row0);
+            }
             else ptx::tma_store_2d(&tmap_out, stg, n, row0);
             ptx::bulk_commit_group();
           }

@@ -150,6 +150,7 @@ struct qasr_handle {
   // hidden-state calls: the lane whose residual stream holds the last qasr_encode_audio_hidden result, and its row count
   Lane* hidden_lane = nullptr;
   long long hidden_tokens = 0;
+  int l2_hints = 0;  // QASR_L2_HINTS bit mask: 1 A evict-first on last use, 2 weights evict-last, 4 residual evict-last, 8 attention q/k/v evict-first
   bool serpentine = true;  // QASR_SERPENTINE=0: every kernel walks the rows upwards
   bool use_graphs = true;
   size_t graph_cap = 64;  // cached whole-call graphs (QASR_GRAPH_CACHE); a ragged job cycles through one graph per sub-batch
@@ -492,9 +493,15 @@ int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __
 
 template <int EPI>
 int dense(qasr_handle* h, int cat, const CUtensorMap& ta, const WeightMaps& tw, int M, int N, int K, void* out,
-          long long ldo, const float* bias, cudaStream_t st, int reverse = 0) {
+          long long ldo, const float* bias, cudaStream_t st, int reverse = 0, bool last_use_of_a = false) {
   GemmParams p = dense_params(M, N, K, out, ldo, bias);
   p.reverse_tiles = reverse;
+  if (h->l2_hints) {
+    const int m = h->l2_hints;  // bit 0: A evict-first on its last use, bit 1: B evict-last, bit 2: residual evict-last
+    if ((m & 1) && last_use_of_a) p.a_policy = ptx::kL2EvictFirst;
+    if (m & 2) p.b_policy = ptx::kL2EvictLast;
+    if ((m & 4) && EPI == EPI_RESID_F32) p.out_policy = ptx::kL2EvictLast;
+  }
   CUtensorMap tout;
   const CUtensorMap* toutp = nullptr;
   // dense outputs leave through a TMA tile store / reduce (exact row count: rows >= M are clipped by the map)
@@ -720,14 +727,15 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
   for (size_t li = 0; li < h->layers.size(); ++li) {
     LayerWeights& L = h->layers[li];
     if ((rc = layernorm(h, x, L.ln1g, L.ln1b, xn, ni, st, next_dir()))) return rc;
-    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, ln.tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_STORE_BF16>(h, QASR_PROF_GEMM_QKV, ln.tm_xn, L.tm_wqkv, ni, 3 * D, D, qkv, 3 * D, L.bqkv, st, next_dir(), true))) return rc;
     {
       ProfScope ps(h, QASR_PROF_ATTENTION, st, attn_flops, 8.0 * n * D);
       if (h->attn_tc) {
         const long long items = nwin * H;
         const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
         window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(ln.tm_qkv, static_cast<const WindowDesc*>(ln.d_windows.p),
-                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e, next_dir());
+                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e, next_dir(),
+                                                                      (h->l2_hints & 8) ? ptx::kL2EvictFirst : 0ull);
       } else {
         next_dir();
         window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
@@ -735,10 +743,10 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
       }
     }
     QCUDA(h, cudaGetLastError());
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, ln.tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_OPROJ, ln.tm_attn, L.tm_wo, ni, D, D, x, D, L.bo, st, next_dir(), true))) return rc;
     if ((rc = layernorm(h, x, L.ln2g, L.ln2b, xn, ni, st, next_dir()))) return rc;
-    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, ln.tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st, next_dir()))) return rc;
-    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, ln.tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st, next_dir()))) return rc;
+    if ((rc = dense<EPI_GELU_BF16>(h, QASR_PROF_GEMM_FC1, ln.tm_xn, L.tm_w1, ni, F, D, hb, F, L.b1, st, next_dir(), true))) return rc;
+    if ((rc = dense<EPI_RESID_F32>(h, QASR_PROF_GEMM_FC2, ln.tm_h, L.tm_w2, ni, D, F, x, D, L.b2, st, next_dir(), true))) return rc;
     if (h->debug && li == 0)
       QCUDA(h, cudaMemcpyAsync(h->dbg_layer0.p, x, static_cast<size_t>(n) * D * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -856,6 +864,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
   if (const char* sp = getenv("QASR_SERPENTINE")) h->serpentine = atoi(sp) != 0;
+  if (const char* lh = getenv("QASR_L2_HINTS")) h->l2_hints = atoi(lh);
   if (const char* gc = getenv("QASR_GRAPH_CACHE")) h->graph_cap = static_cast<size_t>(atoi(gc) > 1 ? atoi(gc) : 1);
   if (const char* mo = getenv("QASR_MEL_ONE_PASS")) h->mel_one_pass = atoi(mo) != 0;
   if (const char* ls = getenv("QASR_LANES")) h->two_lanes = atoi(ls) >= 2;
