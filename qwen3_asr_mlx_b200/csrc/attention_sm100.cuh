@@ -80,6 +80,8 @@ window_attention_sm100(const __grid_constant__ CUtensorMap tmap_qkv, const Windo
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  ptx::grid_dep_wait();  // programmatic dependent launch: q/k/v are valid from here
+  ptx::grid_dep_launch();
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       __nv_bfloat16* __restrict__ y, int rows, float eps, int reverse = 0) {
   constexpr int D = 128 * VPL;
+  ptx::grid_dep_wait();  // programmatic dependent launch (no-op otherwise): x is valid from here
+  ptx::grid_dep_launch();
   const int row_fwd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row_fwd >= rows) return;
@@ -226,6 +228,8 @@ conv1_gelu_tc_kernel(const float* __restrict__ mel, const ChunkDesc* __restrict_
   constexpr int IW = 104;
   __shared__ float in[2 * kConv1RowsPerCta + 1][IW];
 
+  ptx::grid_dep_wait();  // programmatic dependent launch (no-op otherwise): mel, maxima and chunk table are valid from here
+  ptx::grid_dep_launch();
   const int b = blockIdx.x / (64 / kConv1RowsPerCta);
   const int part = blockIdx.x % (64 / kConv1RowsPerCta);
   const int oh0 = part * kConv1RowsPerCta;

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction (driver entry point resolved at
 // run time, so libqasr.so does not link libcuda) and typed launch wrappers.
 #pragma once
+#include <stdlib.h>
 #include <string>
 
 #include "gemm_sm100.cuh"
@@ -106,6 +107,30 @@ inline int gemm_num_sms() {
   return v;
 }
 
+// Programmatic dependent launch (QASR_PDL, default on): kernels that call ptx::grid_dep_wait() are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so their prologue overlaps the tail of the previous kernel in the stream
+// (also inside captured graphs, where the edge becomes a programmatic dependency).
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("QASR_PDL") && atoi(getenv("QASR_PDL")) == 0);
+  return on;
+}
+// <<<grid, block, smem, stream>>> with the PDL attribute; only for kernels that execute grid_dep_wait() before they touch
+// global data.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int BLOCK_N, int kStages, int kAMode, int kEpi, int kCta = 1, bool kDbg = false>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
                                const CUtensorMap* tout = nullptr, int max_ctas = 0) {
@@ -126,24 +151,28 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, Gem
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   grid = (grid / kCta) * kCta;
   if (tiles * kCta < grid) grid = tiles * kCta;
-  if constexpr (kCta == 1) {
-    kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, tout ? *tout : ta, p);
-    return cudaGetLastError();
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = L::kTotal;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCta;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if constexpr (kCta == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = kCta;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, p);
 }
 
 // Plain dense GEMM parameter block: A [M,K] row-major, W [N,K] row-major.

@@ -167,6 +167,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: the prologue above ran beside the previous kernel's tail; operands are valid from here
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -102,6 +102,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running: everything up to grid_dep_wait() (barrier init, TMEM allocation, descriptor prefetch -- nothing that touches
+// global data) overlaps the predecessor's tail; grid_dep_wait() returns once the predecessor has completed and its writes
+// are visible.  grid_dep_launch() lets THIS kernel's dependent start its own prologue.  Both are no-ops in a kernel that was
+// launched without the attribute / has no dependent.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* t) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(t)) : "memory");

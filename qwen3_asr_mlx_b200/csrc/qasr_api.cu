@@ -472,7 +472,8 @@ template <int VPL>
 void launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st, int reverse) {
   // 4 warps per CTA (8 K registers): small enough to co-reside with a persistent GEMM CTA of the other lane
   static const int ln_threads = getenv("QASR_LN_THREADS") ? atoi(getenv("QASR_LN_THREADS")) : 256;
-  layernorm_bf16_kernel<VPL><<<(rows + ln_threads / 32 - 1) / (ln_threads / 32), ln_threads, 0, st>>>(x, g, b, y, rows, 1e-5f, reverse);
+  launch_pdl(layernorm_bf16_kernel<VPL>, dim3((rows + ln_threads / 32 - 1) / (ln_threads / 32)), dim3(ln_threads), 0, st, x, g, b, y, rows, 1e-5f,
+             reverse);
 }
 int layernorm(qasr_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, cudaStream_t st, int reverse = 0) {
   ProfScope ps(h, QASR_PROF_LAYERNORM, st, 0.0, 6.0 * rows * h->cfg.d_model);
@@ -665,9 +666,9 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
             mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w, h->conv1_b,
             static_cast<__nv_bfloat16*>(ln.planes1.p), ps1, utt_max);
       else
-        conv1_gelu_tc_kernel<kStemC><<<g * (64 / kConv1RowsPerCta), kConv1TcThreads, 0, st>>>(
-            mel_dev, static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
-            static_cast<__nv_bfloat16*>(ln.planes1.p), ps1, utt_max);
+        launch_pdl(conv1_gelu_tc_kernel<kStemC>, dim3(g * (64 / kConv1RowsPerCta)), dim3(kConv1TcThreads), 0, st, mel_dev,
+                   static_cast<const ChunkDesc*>(ln.d_chunks.p), static_cast<int>(c0), h->conv1_w_bf16, h->conv1_b,
+                   static_cast<__nv_bfloat16*>(ln.planes1.p), ps1, utt_max);
     }
     QCUDA(h, cudaGetLastError());
     {  // conv2: (g,64,50,480) -> (g,32,25,480), output scattered into conv3's parity planes
@@ -733,9 +734,9 @@ int encode_lane(qasr_handle* h, Lane& ln, const float* mel_dev, const long long*
       if (h->attn_tc) {
         const long long items = nwin * H;
         const int grid = static_cast<int>(items < gemm_num_sms() ? items : gemm_num_sms());
-        window_attention_sm100<<<grid, kAtThreads, kAtSmemBytes, st>>>(ln.tm_qkv, static_cast<const WindowDesc*>(ln.d_windows.p),
-                                                                      static_cast<int>(nwin), H, D, attn, scale_log2e, next_dir(),
-                                                                      (h->l2_hints & 8) ? ptx::kL2EvictFirst : 0ull);
+        launch_pdl(window_attention_sm100, dim3(grid), dim3(kAtThreads), kAtSmemBytes, st, ln.tm_qkv,
+                   static_cast<const WindowDesc*>(ln.d_windows.p), static_cast<int>(nwin), H, D, attn, scale_log2e, next_dir(),
+                   (h->l2_hints & 8) ? ptx::kL2EvictFirst : 0ull);
       } else {
         next_dir();
         window_attention_kernel<<<dim3(static_cast<unsigned>(nwin), H), kAttnThreads, 0, st>>>(
