@@ -114,3 +114,104 @@ def test_window_shares_tile_the_utterance_on_the_window_grid(T, world):
     assert sum(launcher.tokens_for_samples((b - a) * 160) for a, b in shares if b > a) == launcher.tokens_for_samples(T * 160)
     n_win = [-(-(b - a) // 800) for a, b in shares]
     assert max(n_win) - min(n_win) <= 1
+
+
+class _RecordingGather:
+    """PeerBlockGather protocol without any device: records the pushed row blocks."""
+
+    def __init__(self, rows, dim, n_peers):
+        import torch
+
+        self.buf = torch.full((rows, dim), -1.0)
+        self.dtype = torch.float32
+        self.peers = list(range(n_peers))
+        self.pushed = []
+
+    def begin(self):
+        self.pushed = []
+
+    def rows(self, row0, n):
+        return self.buf[row0: row0 + n]
+
+    def push(self, row0, n):
+        self.pushed.append((row0, n))
+
+    def finish(self, total):
+        return self.buf[:total]
+
+
+class _RowIdEncoder:
+    """Writes the GLOBAL token index of this rank's share into every output row (feature 0), through both the one-call path
+    and the hidden-state + row-block projector path of the launcher."""
+
+    class config:
+        output_dim = 2
+
+    def __init__(self):
+        self.calls = []
+
+    def _fill(self, soffs, out, start):
+        import torch
+
+        n = sum(launcher.tokens_for_samples(int(b - a)) for a, b in zip(soffs[:-1], soffs[1:]))
+        out[:n, 0] = torch.arange(start, start + n, dtype=torch.float32)
+        out[:n, 1] = 7.0
+        return n
+
+    def encode_packed_audio(self, audio, soffs, out_dtype="float32", out=None):
+        n = self._fill(soffs, out, int(audio[0]))
+        self.calls.append(("full", n))
+        return out, np.array([0, n])
+
+    def encode_packed_audio_hidden(self, audio, soffs):
+        import torch
+
+        n = sum(launcher.tokens_for_samples(int(b - a)) for a, b in zip(soffs[:-1], soffs[1:]))
+        self._hidden = torch.zeros((n, 2))
+        self._fill(soffs, self._hidden, int(audio[0]))
+        self.calls.append(("hidden", n))
+        return n, np.array([0, n])
+
+    def project_rows(self, row0, out):
+        out.copy_(self._hidden[row0: row0 + out.shape[0]])
+        self.calls.append(("block", int(out.shape[0])))
+        return out
+
+
+@settings(max_examples=120, deadline=None)
+@given(seconds=st.lists(st.integers(min_value=1, max_value=30), min_size=1, max_size=40), world=st.integers(min_value=1, max_value=4),
+       rank_seed=st.integers(min_value=0, max_value=3), budget=st.integers(min_value=50, max_value=2000),
+       tail_blocks=st.integers(min_value=1, max_value=6), tail_min=st.integers(min_value=1, max_value=600))
+def test_contiguous_sharded_pushes_cover_the_share_exactly_once(seconds, world, rank_seed, budget, tail_blocks, tail_min):
+    """Whatever the sub-batch budget and the tail blocking: the pushed blocks tile this rank's rows exactly once, in order, the
+    last sub-batch (and only it) goes through the hidden-state path when it is split, and every row holds what its token
+    produced."""
+    import torch
+
+    rank = rank_seed % world
+    n_samples = [16000 * s + 37 for s in seconds]
+    costs = [launcher.tokens_for_samples(n) for n in n_samples]
+    offsets = np.concatenate([[0], np.cumsum(costs)])
+    mine = launcher.contiguous_partition(costs, world)[rank]
+    if not mine:
+        return
+    row_base, my_rows = int(offsets[mine[0]]), int(sum(costs[i] for i in mine))
+    # the fake "audio": the first sample of every sub-batch slice must tell the encoder the global row it starts at, so fill each
+    # utterance's samples with the global token offset of that utterance
+    packed = torch.cat([torch.full((n_samples[i],), float(offsets[i])) for i in mine])
+    g = _RecordingGather(int(offsets[-1]), 2, n_peers=world - 1)
+    enc = _RowIdEncoder()
+    emb, offs, got_mine = launcher.encode_contiguous_sharded(enc, packed, n_samples, rank, world, gather=g, tokens_per_call=budget,
+                                                             out_dtype="float32", tail_blocks=tail_blocks, tail_min_rows=tail_min)
+    assert got_mine == mine and list(offs) == list(offsets)
+    pos = row_base
+    for r0, n in g.pushed:  # contiguous, ordered, no gap, no overlap
+        assert r0 == pos and n > 0
+        pos += n
+    assert pos == row_base + my_rows
+    assert torch.equal(emb[row_base: row_base + my_rows, 0], torch.arange(row_base, row_base + my_rows, dtype=torch.float32))
+    kinds = [k for k, _ in enc.calls]
+    if "hidden" in kinds:  # only the LAST sub-batch is split, and only when there is a peer to push to
+        assert world > 1 and kinds.index("hidden") == len([k for k in kinds if k == "full"]) and kinds.count("hidden") == 1
+        blocks = [n for k, n in enc.calls if k == "block"]
+        assert 2 <= len(blocks) <= tail_blocks and sum(blocks) == dict(enc.calls)["hidden"]
