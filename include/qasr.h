@@ -6,6 +6,7 @@
  *   qasr_mel*            log_mel_spectrogram(audio)                 src/qwen3_asr_mlx/audio.py:238-278
  *   qasr_encode*         AudioEncoder.__call__(mel)                 src/qwen3_asr_mlx/encoder.py:235-323
  *   qasr_encode_audio*   the back-to-back call site                 src/qwen3_asr_mlx/model.py:331-335, 418-420
+ *   qasr_encode_audio_hidden + qasr_project_rows   the same call split in front of the projector (encoder.py:235-317 | 319-321)
  *   qasr_create          AudioEncoder.__init__(config)              src/qwen3_asr_mlx/encoder.py:142-191
  *   qasr_set_weight      load_encoder_weights / model.load_weights  src/qwen3_asr_mlx/encoder.py:330-359
  *   qasr_count_tokens    AudioEncoder._conv_output_length + chunking src/qwen3_asr_mlx/encoder.py:197-207,258-268
