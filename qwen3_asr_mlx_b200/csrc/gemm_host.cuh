@@ -110,10 +110,13 @@ inline int gemm_num_sms() {
 // Programmatic dependent launch (QASR_PDL, default on): kernels that call ptx::grid_dep_wait() are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so their prologue overlaps the tail of the previous kernel in the stream
 // (also inside captured graphs, where the edge becomes a programmatic dependency).
-inline bool pdl_enabled() {
-  static const bool on = !(getenv("QASR_PDL") && atoi(getenv("QASR_PDL")) == 0);
+inline bool& pdl_flag() {
+  static bool on = !(getenv("QASR_PDL") && atoi(getenv("QASR_PDL")) == 0);
   return on;
 }
+inline bool pdl_enabled() { return pdl_flag(); }
+// re-read QASR_PDL (every qasr_create does: the switch is process-wide because launch_gemm is shared with the decoder)
+inline void pdl_refresh_from_env() { pdl_flag() = !(getenv("QASR_PDL") && atoi(getenv("QASR_PDL")) == 0); }
 // <<<grid, block, smem, stream>>> with the PDL attribute; only for kernels that execute grid_dep_wait() before they touch
 // global data.
 template <typename... KArgs, typename... Args>

@@ -865,6 +865,7 @@ int qasr_create(int device, const qasr_config* cfg, qasr_handle** out) {
   }
   if (const char* gr = getenv("QASR_GRAPHS")) h->use_graphs = atoi(gr) != 0;
   if (const char* sp = getenv("QASR_SERPENTINE")) h->serpentine = atoi(sp) != 0;
+  pdl_refresh_from_env();
   if (const char* lh = getenv("QASR_L2_HINTS")) h->l2_hints = atoi(lh);
   if (const char* gc = getenv("QASR_GRAPH_CACHE")) h->graph_cap = static_cast<size_t>(atoi(gc) > 1 ? atoi(gc) : 1);
   if (const char* mo = getenv("QASR_MEL_ONE_PASS")) h->mel_one_pass = atoi(mo) != 0;

