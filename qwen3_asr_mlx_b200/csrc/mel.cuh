@@ -153,55 +153,80 @@ struct MelSmem {
   short fb_start[kMelBins];
   short fb_count[kMelBins];
   float red[(kMelThreads + 31) / 32];
+  int next_tile;
 };
 
+// Where a tile (32 frames of one utterance) lives: resolved from the tile index by a binary search over the per-utterance tile
+// offsets (warp-uniform, a handful of L1-resident loads).
+struct MelTile {
+  int u, T, t0, nf, span;
+  long long N, f0, first;
+  const float* x;
+  __device__ __forceinline__ bool interior() const { return first >= 0 && first + span <= N; }
+};
+__device__ __forceinline__ MelTile mel_tile(int tile, const float* __restrict__ audio, const long long* __restrict__ sample_offsets,
+                                            const long long* __restrict__ frame_offsets, const int* __restrict__ block_offsets, int B) {
+  MelTile t;
+  t.u = upper_segment<int>(block_offsets, B, tile);
+  const long long s0 = __ldg(sample_offsets + t.u);
+  t.N = __ldg(sample_offsets + t.u + 1) - s0;
+  t.f0 = __ldg(frame_offsets + t.u);
+  t.T = static_cast<int>(__ldg(frame_offsets + t.u + 1) - t.f0);
+  t.t0 = (tile - __ldg(block_offsets + t.u)) * kMelFramesPerCta;
+  t.nf = min(kMelFramesPerCta, t.T - t.t0);
+  t.span = (t.nf - 1) * kMelHop + kMelNfft;
+  t.first = static_cast<long long>(t.t0) * kMelHop - kMelNfft / 2;
+  t.x = audio + s0;
+  return t;
+}
+
+// A warp copies whole hops (160 samples -> 161 padded words of `raw`): hops warp, warp + 9, ... of the tile's span, five
+// coalesced loads per hop.  The loads of an INTERIOR tile (no reflection) go to registers first, so that they can be issued one
+// tile ahead (mel_prefetch) and land while the current tile is still computing.
+constexpr int kMelHopsPerWarp = ((kMelFramesPerCta - 1) * kMelHop + kMelNfft + kMelHop - 1) / kMelHop / (kMelThreads / 32) + 1;  // 4
+struct MelPrefetch {
+  float v[kMelHopsPerWarp][kMelHop / 32];
+};
+__device__ __forceinline__ void mel_prefetch(const MelTile& t, MelPrefetch& r, int tid) {
+  const float* __restrict__ src = t.x + t.first;
+#pragma unroll
+  for (int h = 0; h < kMelHopsPerWarp; ++h) {
+    const int hop = (tid >> 5) + h * (kMelThreads / 32);
+    const int left = t.span - hop * kMelHop;
+#pragma unroll
+    for (int k = 0; k < kMelHop / 32; ++k) {
+      const int i = (tid & 31) + 32 * k;
+      r.v[h][k] = (i < left) ? __ldg(src + hop * kMelHop + i) : 0.0f;
+    }
+  }
+}
+__device__ __forceinline__ void mel_store_prefetched(const MelTile& t, const MelPrefetch& r, float* __restrict__ raw, int tid) {
+#pragma unroll
+  for (int h = 0; h < kMelHopsPerWarp; ++h) {
+    const int hop = (tid >> 5) + h * (kMelThreads / 32);
+    const int left = t.span - hop * kMelHop;
+#pragma unroll
+    for (int k = 0; k < kMelHop / 32; ++k) {
+      const int i = (tid & 31) + 32 * k;
+      if (i < left) raw[hop * (kMelHop + 1) + i] = r.v[h][k];
+    }
+  }
+}
+
+// Persistent CTAs (two per SM): the tables are staged once per CTA, tiles are taken round-robin, and the raw samples of the
+// NEXT tile are fetched into registers between step A and step C of the current one (ncu before: a third of the stall samples
+// sat on the shared-memory stores waiting for a tile's own global loads, and a sixth of the instructions re-staged the tables).
 __global__ void __launch_bounds__(kMelThreads)
 mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ sample_offsets,
                   const long long* __restrict__ frame_offsets, const int* __restrict__ block_offsets, int B,
-                  MelTables tab, float* __restrict__ mel_out, unsigned* __restrict__ utt_max) {
+                  MelTables tab, float* __restrict__ mel_out, unsigned* __restrict__ utt_max /* [B] maxima, [B] tile counter (0) */) {
   extern __shared__ __align__(16) uint8_t mel_smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(mel_smem_raw);
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  unsigned* __restrict__ tile_counter = utt_max + B;  // tiles beyond the first gridDim.x are handed out dynamically
+  const int total_tiles = __ldg(block_offsets + B);
 
-  const int u = upper_segment<int>(block_offsets, B, static_cast<int>(blockIdx.x));
-  const long long s0 = __ldg(sample_offsets + u);
-  const long long N = __ldg(sample_offsets + u + 1) - s0;
-  const long long f0 = __ldg(frame_offsets + u);
-  const int T = static_cast<int>(__ldg(frame_offsets + u + 1) - f0);
-  const int t0 = (static_cast<int>(blockIdx.x) - __ldg(block_offsets + u)) * kMelFramesPerCta;
-  const int nf = min(kMelFramesPerCta, T - t0);
-
-  // ---- stage tables and the reflect-padded sample span of these frames
-  const int span = (nf - 1) * kMelHop + kMelNfft;
-  const long long first = static_cast<long long>(t0) * kMelHop - kMelNfft / 2;
-  const float* __restrict__ x = audio + s0;
-  if (first >= 0 && first + span <= N) {
-    // interior tile (the common case): no reflection.  A warp copies whole hops (160 samples -> 161 padded words), five
-    // coalesced loads in flight per thread and no per-sample index division.
-    const float* __restrict__ src = x + first;
-    for (int hop = tid >> 5; hop * kMelHop < span; hop += kMelThreads / 32) {
-      const float* __restrict__ sp = src + hop * kMelHop;
-      float* __restrict__ dp = s.raw + hop * (kMelHop + 1);
-      const int left = span - hop * kMelHop;
-      float v[kMelHop / 32];
-#pragma unroll
-      for (int k = 0; k < kMelHop / 32; ++k) {
-        const int i = (tid & 31) + 32 * k;
-        v[k] = (i < left) ? __ldg(sp + i) : 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < kMelHop / 32; ++k) {
-        const int i = (tid & 31) + 32 * k;
-        if (i < left) dp[i] = v[k];
-      }
-    }
-  } else {
-    for (int i = tid; i < span; i += kMelThreads) {
-      long long j = first + i;
-      if (j < 0 || j >= N) j = reflect_index(j, N);
-      s.raw[i + i / kMelHop] = __ldg(x + j);
-    }
-  }
   for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
   for (int i = tid; i < 9 * 25; i += kMelThreads) s.twiddle[i] = __ldg(tab.twiddle + i);
   for (int i = tid; i < kMelBins * kMelMaxTaps; i += kMelThreads) s.fb_weight[i] = __ldg(tab.fb_weight + i);
@@ -209,12 +234,34 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
     s.fb_start[i] = static_cast<short>(__ldg(tab.fb_start + i));
     s.fb_count[i] = static_cast<short>(__ldg(tab.fb_count + i));
   }
+
+  MelPrefetch pre;
+  bool pre_valid = false;
+  int tile = static_cast<int>(blockIdx.x);
+  if (tile < total_tiles) {
+    const MelTile t = mel_tile(tile, audio, sample_offsets, frame_offsets, block_offsets, B);
+    if (t.interior()) { mel_prefetch(t, pre, tid); pre_valid = true; }
+  }
+  while (tile < total_tiles) {
+  const MelTile tl = mel_tile(tile, audio, sample_offsets, frame_offsets, block_offsets, B);
+  const int u = tl.u, T = tl.T, t0 = tl.t0, nf = tl.nf;
+  const long long f0 = tl.f0;
+
+  // ---- stage the reflect-padded sample span of these frames
+  if (pre_valid) {
+    mel_store_prefetched(tl, pre, s.raw, tid);
+  } else {
+    for (int i = tid; i < tl.span; i += kMelThreads) {
+      long long j = tl.first + i;
+      if (j < 0 || j >= tl.N) j = reflect_index(j, tl.N);
+      s.raw[i + i / kMelHop] = __ldg(tl.x + j);
+    }
+  }
   __syncthreads();
 
   // Every step maps the tile's frames onto lanes (lane = frame) and one unit of work onto a warp, so that table lookups
   // (window, twiddles, filter taps) are warp-uniform broadcasts, branches are uniform and every shared-memory access of a
   // warp hits 32 different banks (ncu on the previous task-major mapping: 30 % of the LSU wavefronts were bank conflicts).
-  const int lane = tid & 31, warp = tid >> 5;
   // ---- step A/B: 25 real 16-point DFTs per frame, twiddled; warp = input residue n2 (3 rounds of 9 warps)
   for (int n2 = warp; n2 < 25; n2 += kMelThreads / 32) {
     if (lane < nf) {
@@ -239,7 +286,17 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
       }
     }
   }
+  if (tid == 0) s.next_tile = static_cast<int>(gridDim.x + atomicAdd(tile_counter, 1u));  // tiles differ in cost (ragged ends, reflection)
   __syncthreads();
+
+  // ---- the raw samples are dead from here (P aliases them): fetch the next tile's into registers; they land during step C
+  // and the filterbank
+  const int next = s.next_tile;
+  pre_valid = false;
+  if (next < total_tiles) {
+    const MelTile nx = mel_tile(next, audio, sample_offsets, frame_offsets, block_offsets, B);
+    if (nx.interior()) { mel_prefetch(nx, pre, tid); pre_valid = true; }
+  }
 
   // ---- step C: 9 complex 25-point DFTs per frame -> power spectrum P[bin][frame]; warp = k1 (one round)
   if (lane < nf) {
@@ -292,7 +349,7 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
       // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here.
       // A non-finite sample makes its frames NaN in the reference (np.maximum / .max() propagate NaN, audio.py:274-275)
       // and, through the utterance-wide max, the whole utterance: NaN is carried, not dropped by fmaxf.
-      const float v = (acc != acc) ? kMelNaN : __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+      const float v = (acc != acc) ? kMelNaN : __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;  // (kept: bit-identical to round 1)
       out[static_cast<long long>(m) * T + t0 + lane] = v;
       lmax = nan_max(lmax, v);
     }
@@ -307,6 +364,9 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
     for (int i = 1; i < (kMelThreads + 31) / 32; ++i) m = nan_max(m, s.red[i]);
     atomicMax(utt_max + u, float_to_ordered(m));
   }
+  __syncthreads();  // the next tile overwrites raw / P and the reduction scratch
+  tile = next;
+  }  // tile loop
 }
 
 // Pass 2: x = (max(x, utt_max - 8) + 4) / 4 over the packed mel buffer (float4 granularity:

@@ -369,7 +369,7 @@ int ensure_batch_tables(qasr_handle* h, long long batch) {
     if ((rc = dev_alloc(h, h->d_soffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
     if ((rc = dev_alloc(h, h->d_foffs, static_cast<size_t>(batch + 1) * 8, false))) return rc;
     if ((rc = dev_alloc(h, h->d_boffs, static_cast<size_t>(batch + 1) * 4, false))) return rc;
-    if ((rc = dev_alloc(h, h->d_uttmax, static_cast<size_t>(batch) * 4, false))) return rc;
+    if ((rc = dev_alloc(h, h->d_uttmax, static_cast<size_t>(batch + 1) * 4, false))) return rc;  // + the mel kernel's tile counter
     h->cap_batch = batch;
   }
   return QASR_OK;
@@ -553,12 +553,13 @@ int mel_impl(qasr_handle* h, const float* audio_dev, const int64_t* sample_offse
   QCUDA(h, cudaMemcpyAsync(h->d_soffs.p, pin, b8, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_foffs.p, pin + b8, b8, cudaMemcpyHostToDevice, st));
   QCUDA(h, cudaMemcpyAsync(h->d_boffs.p, pin + 2 * b8, b4, cudaMemcpyHostToDevice, st));
-  QCUDA(h, cudaMemsetAsync(h->d_uttmax.p, 0, static_cast<size_t>(B) * 4, st));
+  QCUDA(h, cudaMemsetAsync(h->d_uttmax.p, 0, static_cast<size_t>(B + 1) * 4, st));
 
   MelTables tab{h->d_window, h->d_twiddle, h->d_fb_start, h->d_fb_count, h->d_fb_weight};
   {  // algorithmic bytes: audio read once + log-mel written once (115 200 B per audio-second)
     ProfScope ps(h, QASR_PROF_MEL_LOGMEL, st, 0.0, 4.0 * soffs[B] + 4.0 * kMelBins * foffs[B]);
-    mel_logmel_kernel<<<boffs[B], kMelThreads, sizeof(MelSmem), st>>>(
+    const int mel_grid = boffs[B] < 2 * gemm_num_sms() ? boffs[B] : 2 * gemm_num_sms();  // persistent: two CTAs per SM
+    mel_logmel_kernel<<<mel_grid, kMelThreads, sizeof(MelSmem), st>>>(
         audio_dev, static_cast<const long long*>(h->d_soffs.p), static_cast<const long long*>(h->d_foffs.p),
         static_cast<const int*>(h->d_boffs.p), B, tab, mel_dev, static_cast<unsigned*>(h->d_uttmax.p));
   }
