@@ -150,8 +150,7 @@ struct MelSmem {
   float2 twiddle[9 * 25];
   float2 Y[kMelFramesPerCta][9][25];
   float fb_weight[kMelBins * kMelMaxTaps];
-  short fb_start[kMelBins];
-  short fb_count[kMelBins];
+  int fb_band[kMelBins];  // start | count << 16
   float red[(kMelThreads + 31) / 32];
   int next_tile;
 };
@@ -230,10 +229,7 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   for (int i = tid; i < kMelNfft; i += kMelThreads) s.window[i] = __ldg(tab.window + i);
   for (int i = tid; i < 9 * 25; i += kMelThreads) s.twiddle[i] = __ldg(tab.twiddle + i);
   for (int i = tid; i < kMelBins * kMelMaxTaps; i += kMelThreads) s.fb_weight[i] = __ldg(tab.fb_weight + i);
-  for (int i = tid; i < kMelBins; i += kMelThreads) {
-    s.fb_start[i] = static_cast<short>(__ldg(tab.fb_start + i));
-    s.fb_count[i] = static_cast<short>(__ldg(tab.fb_count + i));
-  }
+  for (int i = tid; i < kMelBins; i += kMelThreads) s.fb_band[i] = __ldg(tab.fb_start + i) | (__ldg(tab.fb_count + i) << 16);
 
   MelPrefetch pre;
   bool pre_valid = false;
@@ -323,10 +319,13 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   // All taps of a bin are loaded before the FMA chain starts (the tap count is warp-uniform), so a round costs one
   // shared-memory latency instead of one per tap; the summation order is unchanged.
   float lmax = -INFINITY;
-  float* __restrict__ out = mel_out + f0 * kMelBins;
-  for (int m = warp; m < kMelBins; m += kMelThreads / 32) {
+  // this lane's output column; advanced by one warp-round of mel rows per iteration (no 64-bit multiply per bin)
+  float* __restrict__ out = mel_out + f0 * kMelBins + static_cast<long long>(warp) * T + t0 + lane;
+  const long long out_step = static_cast<long long>(kMelThreads / 32) * T;
+  for (int m = warp; m < kMelBins; m += kMelThreads / 32, out += out_step) {
     if (lane < nf) {
-      const int st = s.fb_start[m], cnt = s.fb_count[m];
+      const int band = s.fb_band[m];
+      const int st = band & 0xFFFF, cnt = band >> 16;
       const float* w = s.fb_weight + m * kMelMaxTaps;
       const float* pcol = &s.P[st][lane];
       float acc = 0.0f;
@@ -349,8 +348,11 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
       // log10(x) = log2(x) * log10(2); lg2.approx is accurate to ~2^-22 relative, i.e. < 2e-6 absolute here.
       // A non-finite sample makes its frames NaN in the reference (np.maximum / .max() propagate NaN, audio.py:274-275)
       // and, through the utterance-wide max, the whole utterance: NaN is carried, not dropped by fmaxf.
-      const float v = (acc != acc) ? kMelNaN : __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;  // (kept: bit-identical to round 1)
-      out[static_cast<long long>(m) * T + t0 + lane] = v;
+      // the argument is >= 1e-10, a normal number: the .ftz form gives the same bits as __log2f without its subnormal rescue
+      float lg;
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(acc, 1e-10f)));
+      const float v = (acc != acc) ? kMelNaN : lg * 0.30102999566398120f;
+      *out = v;
       lmax = nan_max(lmax, v);
     }
   }
