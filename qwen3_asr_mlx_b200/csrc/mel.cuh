@@ -180,14 +180,14 @@ __device__ __forceinline__ MelTile mel_tile(int tile, const float* __restrict__ 
 }
 
 // A warp copies whole hops (160 samples -> 161 padded words of `raw`): hops warp, warp + 9, ... of the tile's span, five
-// coalesced loads per hop.  The loads of an INTERIOR tile (no reflection) go to registers first, so that they can be issued one
-// tile ahead (mel_prefetch) and land while the current tile is still computing.
+// coalesced loads per hop.  The loads go to registers first, so that they can be issued one tile ahead (mel_prefetch) and land
+// while the current tile is still computing; the tiles at the ends of an utterance reflect their out-of-range indices.
 constexpr int kMelHopsPerWarp = ((kMelFramesPerCta - 1) * kMelHop + kMelNfft + kMelHop - 1) / kMelHop / (kMelThreads / 32) + 1;  // 4
 struct MelPrefetch {
   float v[kMelHopsPerWarp][kMelHop / 32];
 };
-__device__ __forceinline__ void mel_prefetch(const MelTile& t, MelPrefetch& r, int tid) {
-  const float* __restrict__ src = t.x + t.first;
+template <bool kReflect>
+__device__ __forceinline__ void mel_prefetch_impl(const MelTile& t, MelPrefetch& r, int tid) {
 #pragma unroll
   for (int h = 0; h < kMelHopsPerWarp; ++h) {
     const int hop = (tid >> 5) + h * (kMelThreads / 32);
@@ -195,9 +195,15 @@ __device__ __forceinline__ void mel_prefetch(const MelTile& t, MelPrefetch& r, i
 #pragma unroll
     for (int k = 0; k < kMelHop / 32; ++k) {
       const int i = (tid & 31) + 32 * k;
-      r.v[h][k] = (i < left) ? __ldg(src + hop * kMelHop + i) : 0.0f;
+      long long j = t.first + hop * kMelHop + i;
+      if (kReflect && (j < 0 || j >= t.N)) j = reflect_index(j, t.N);  // np.pad(mode="reflect"): only the ends of an utterance
+      r.v[h][k] = (i < left) ? __ldg(t.x + j) : 0.0f;
     }
   }
+}
+__device__ __forceinline__ void mel_prefetch(const MelTile& t, MelPrefetch& r, int tid) {
+  if (t.interior()) mel_prefetch_impl<false>(t, r, tid);
+  else mel_prefetch_impl<true>(t, r, tid);
 }
 __device__ __forceinline__ void mel_store_prefetched(const MelTile& t, const MelPrefetch& r, float* __restrict__ raw, int tid) {
 #pragma unroll
@@ -232,27 +238,15 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   for (int i = tid; i < kMelBins; i += kMelThreads) s.fb_band[i] = __ldg(tab.fb_start + i) | (__ldg(tab.fb_count + i) << 16);
 
   MelPrefetch pre;
-  bool pre_valid = false;
   int tile = static_cast<int>(blockIdx.x);
-  if (tile < total_tiles) {
-    const MelTile t = mel_tile(tile, audio, sample_offsets, frame_offsets, block_offsets, B);
-    if (t.interior()) { mel_prefetch(t, pre, tid); pre_valid = true; }
-  }
+  if (tile < total_tiles) mel_prefetch(mel_tile(tile, audio, sample_offsets, frame_offsets, block_offsets, B), pre, tid);
   while (tile < total_tiles) {
   const MelTile tl = mel_tile(tile, audio, sample_offsets, frame_offsets, block_offsets, B);
   const int u = tl.u, T = tl.T, t0 = tl.t0, nf = tl.nf;
   const long long f0 = tl.f0;
 
   // ---- stage the reflect-padded sample span of these frames
-  if (pre_valid) {
-    mel_store_prefetched(tl, pre, s.raw, tid);
-  } else {
-    for (int i = tid; i < tl.span; i += kMelThreads) {
-      long long j = tl.first + i;
-      if (j < 0 || j >= tl.N) j = reflect_index(j, tl.N);
-      s.raw[i + i / kMelHop] = __ldg(tl.x + j);
-    }
-  }
+  mel_store_prefetched(tl, pre, s.raw, tid);
   __syncthreads();
 
   // Every step maps the tile's frames onto lanes (lane = frame) and one unit of work onto a warp, so that table lookups
@@ -288,11 +282,7 @@ mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__
   // ---- the raw samples are dead from here (P aliases them): fetch the next tile's into registers; they land during step C
   // and the filterbank
   const int next = s.next_tile;
-  pre_valid = false;
-  if (next < total_tiles) {
-    const MelTile nx = mel_tile(next, audio, sample_offsets, frame_offsets, block_offsets, B);
-    if (nx.interior()) { mel_prefetch(nx, pre, tid); pre_valid = true; }
-  }
+  if (next < total_tiles) mel_prefetch(mel_tile(next, audio, sample_offsets, frame_offsets, block_offsets, B), pre, tid);
 
   // ---- step C: 9 complex 25-point DFTs per frame -> power spectrum P[bin][frame]; warp = k1 (one round)
   if (lane < nf) {
