@@ -1,7 +1,7 @@
 // Log-mel frontend kernels (reference: log_mel_spectrogram, audio.py:238-278; _stft :211-235;
 // _build_mel_filterbank :41-80).
 //
-// Pass 1 (mel_logmel_kernel): one CTA per 32 frames of one utterance.
+// Pass 1 (mel_logmel_kernel): persistent CTAs, one 32-frame tile of one utterance at a time.
 //   reflect-padded framing -> symmetric Hann window -> 400-point real FFT (16 x 25, fp32,
 //   see mel_fft.cuh) -> power -> banded mel filterbank -> log10(max(., 1e-10)) -> packed
 //   (128, T_u) fp32 output + per-utterance running max (ordered-uint atomicMax).
@@ -218,9 +218,10 @@ __device__ __forceinline__ void mel_store_prefetched(const MelTile& t, const Mel
   }
 }
 
-// Persistent CTAs (two per SM): the tables are staged once per CTA, tiles are taken round-robin, and the raw samples of the
-// NEXT tile are fetched into registers between step A and step C of the current one (ncu before: a third of the stall samples
-// sat on the shared-memory stores waiting for a tile's own global loads, and a sixth of the instructions re-staged the tables).
+// Persistent CTAs (two per SM): the tables are staged once per CTA, tiles beyond the first wave are handed out by an atomic
+// counter (tiles at utterance ends cost less, reflected ones more), and the raw samples of the NEXT tile are fetched into
+// registers between step A and step C of the current one (ncu before: a third of the stall samples sat on the shared-memory
+// stores waiting for a tile's own global loads, and a sixth of the instructions re-staged the tables).
 __global__ void __launch_bounds__(kMelThreads)
 mel_logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ sample_offsets,
                   const long long* __restrict__ frame_offsets, const int* __restrict__ block_offsets, int B,
