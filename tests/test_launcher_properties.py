@@ -215,3 +215,19 @@ def test_contiguous_sharded_pushes_cover_the_share_exactly_once(seconds, world, 
         assert world > 1 and kinds.index("hidden") == len([k for k in kinds if k == "full"]) and kinds.count("hidden") == 1
         blocks = [n for k, n in enc.calls if k == "block"]
         assert 2 <= len(blocks) <= tail_blocks and sum(blocks) == dict(enc.calls)["hidden"]
+
+
+def test_bind_host_to_gpu_never_breaks_the_process():
+    """Without NVML / a GPU the binding is a no-op that reports None; with one it returns a non-empty subset of the cores the
+    process was allowed to use.  Either way the process keeps a usable affinity mask."""
+    import os
+
+    before = os.sched_getaffinity(0)
+    cores = launcher.bind_host_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    assert after and after <= before
+    if cores is None:
+        assert after == before
+    else:
+        assert set(cores) == after
+    os.sched_setaffinity(0, before)
